@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline measurement (BASELINE.json: env-steps/s and rendered frames/s at
+batch N; workload = configs[1]: Breakout, 65,536 envs per GPU, grayscale 84x84 observations, random actions).
+
+One "step" = one pass of the hot path over the whole batch: generate the synthetic action stream on the
+device, advance every env one frame (tbx_step), render every env (tbx_render).  Prints ONE JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--game G] [--envs E] [--obs gray84|gray|rgb|rgba]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
+    python bench.py --impl reference ...    times the CPU restatement of the reference path (oracle/) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GAME_DTYPE = {"breakout": "f64+u8", "amidar": "i32+u8", "space_invaders": "i32+u8"}
+STATE_BYTES = {"breakout": None, "amidar": None, "space_invaders": None}   # filled from the library's record size
+ACTION_SEED = 0xB200
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--game", default="breakout")
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--obs", default="gray84")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def obs_bytes(game, obs):
+    w, h = {"breakout": (240, 160), "amidar": (160, 250), "space_invaders": (320, 210)}[game]
+    return {"gray84": 84 * 84, "gray": w * h, "rgb": w * h * 3, "rgba": w * h * 4}[obs]
+
+
+def workload_name(game, envs, obs):
+    return "%s batched %d envs/GPU, %s obs, uniform random legal actions, auto-reset" % (game, envs, obs)
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_rollout(game, obs, n_envs, steps, threads):
+    """Oracle (CPU restatement of the reference's engine) on `threads` host threads; returns (env-steps/s, seconds)."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    import numpy as np
+    from oracle import oracle as O
+    batch = O.OracleBatch(game, n_envs, seeds=1234 + np.arange(n_envs))
+    batch.rollout(2, 0, ACTION_SEED, 0, obs)               # touch everything once
+    sec, _, _ = batch.rollout(steps, 2, ACTION_SEED, 0, obs)
+    return n_envs * steps / sec, sec
+
+
+def reference_arm(args):
+    """--impl reference: ctoybox itself cannot be installed here (third-party Rust, no network, no rustc), so the
+    reference arm is the CPU oracle -- the restated engine -- run with every host thread on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import numpy as np
+    from oracle import oracle as O
+    n_sample = 256 * cores
+    batch = O.OracleBatch(args.game, n_sample, seeds=1234 + np.arange(n_sample))
+    t = 0
+    for _ in range(max(args.warmup, 1)):
+        batch.rollout(1, t, ACTION_SEED, 0, args.obs)
+        t += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.rollout(1, t, ACTION_SEED, 0, args.obs)
+        t += 1
+    sec = time.perf_counter() - t0
+    value = n_sample * args.steps / sec
+    sample = "%d envs x 1 frame (step + %s render) per step on %d OpenMP threads" % (n_sample, args.obs, cores)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec with rendered frames", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": GAME_DTYPE[args.game], "data": "synthetic",
+        "config": {"workload": workload_name(args.game, args.envs, args.obs), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "ctoybox==0.5.0 (Rust) is not installable here; this is oracle/ (C restatement) on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                if out:
+                    self.samples.append([x.strip() for x in out[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, name in enumerate(names):
+                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import numpy as np
+    import torch
+    import toybox_b200
+    toybox_b200.lib()            # raises if the CUDA library is missing: no fallback
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n = args.envs
+    env0 = rank * n
+    pool = toybox_b200.BatchedToybox(args.game, n, device=dev, obs=args.obs,
+                                     seeds=(1234 + env0 + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF)
+    fb = obs_bytes(args.game, args.obs)
+    obs = torch.empty((n,) + pool.obs_shape, dtype=torch.uint8, device=dev)
+    actions = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(t, ev=None):
+        pool.fill_random_actions(actions, ACTION_SEED, t, env0)
+        if ev is not None:
+            ev[0].record(stream)
+        pool.apply_ale_action(actions, auto_reset=True)
+        if ev is not None:
+            ev[1].record(stream)
+        pool.render(out=obs)
+        if ev is not None:
+            ev[2].record(stream)
+
+    t = 0
+    for _ in range(max(args.warmup, 3)):
+        step(t)
+        t += 1
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for k in range(K):
+        step(t, evs[k])
+        t += 1
+    e_end.record(stream)
+    barrier()
+    ms = e_start.elapsed_time(e_end)
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    pool.check()
+    if dist is not None:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        # the path's one collective: the episode-statistics vector (tens of bytes), summed / maxed over GPUs
+        st = torch.tensor(pool.episode_stats(), dtype=torch.int64, device=dev)
+        mx = st[3:].clone()
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        stats = [int(st[0]), int(st[1]), int(st[2]), int(mx[0])]
+    else:
+        stats = pool.episode_stats()
+    value = world * n * K / (ms * 1e-3)
+
+    # ---- e2e: the same metric through the host-facing call (host actions in, host observations out)
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(rank)
+        legal = np.asarray(pool.get_legal_action_set(), np.int32)
+        h_actions = torch.from_numpy(legal[rng.integers(0, len(legal), size=n)]).pin_memory()
+        h_obs = torch.empty((n,) + pool.obs_shape, dtype=torch.uint8).pin_memory()
+        ke = max(3, min(K, 20))
+        for _ in range(3):
+            pool.step_host(h_actions, obs_out=h_obs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            pool.step_host(h_actions, obs_out=h_obs)
+        barrier()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+        e2e = {"value": world * n * ke / sec, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
+               "d2h_bytes_per_step": n * (fb + 4 + 1 + 4 + 4), "steps": ke,
+               "api": "BatchedToybox.step_host -> tbx_step_host (pinned host actions in; obs, reward, done, score, lives out)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (render): algorithmic bytes per launch / measured launch time
+    rec_bytes = 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game]
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = n * (fb + rec_bytes)          # frame written + state record read, per env, per launch
+    achieved = alg_bytes / (render_ms * 1e-3) / 1e9
+    roofline = {"kernel": "render_kernel<%s,%s>" % (args.game, args.obs), "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": alg_bytes, "launch_ms": render_ms, "step_kernel_ms": step_ms}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_cpu = 64 * cores
+        v1, s1 = cpu_rollout(args.game, args.obs, n_cpu, 20, cores)
+        steps_cpu = int(max(20, min(4000, 12.0 / (s1 / 20))))
+        v, s = cpu_rollout(args.game, args.obs, n_cpu, steps_cpu, cores)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d envs x %d frames (step + %s render), %.1f s, oracle/ C restatement with OpenMP" % (n_cpu, steps_cpu, args.obs, s)}
+    line = {
+        "metric": "env-steps/sec with rendered frames", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": GAME_DTYPE[args.game], "data": "synthetic",
+        "config": {"workload": workload_name(args.game, n, args.obs), "envs_per_gpu": n, "obs_bytes_per_env": fb,
+                   "l2": "each step writes %d MB of observations (> 126 MB L2) between reuses of the %d MB state" %
+                         (n * fb // 2 ** 20, n * rec_bytes // 2 ** 20),
+                   "seeds": "env i: set_seed(1234+i); actions: counter-based stream seed 0xB200"},
+        "frames_per_sec": value, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
+        "launches_per_step": ["fill_actions_kernel", "step_kernel", "render_kernel"],
+        "clocks": clocks, "episode_stats": {"episodes": stats[0], "sum_return": stats[1], "sum_length": stats[2], "max_return": stats[3]},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/* emu.cpp -- TEST-ONLY host build of the engine headers (tbx_breakout.h, tbx_space_invaders.h,
+ * tbx_amidar.h) plus the library's host half (tbx_host.cpp), so the CPU-only test tier can check the
+ * very functions the CUDA kernels are compiled from -- transition, new_game, draw list, INTER_AREA
+ * arithmetic, JSON codecs -- against the oracle without a GPU.  It is NOT part of libtoybox_b200.so and the
+ * product never loads it: the product path has no CPU fallback.
+ *
+ * One `Emu` is one environment (an AoS record, stride 1).  Painting uses a plain sequential painter's
+ * algorithm over the draw list; the kernels' warp-band painter is checked on the GPU tier.
+ */
+#include "../../toybox_b200/csrc/tbx_host.h"
+#include "../../toybox_b200/csrc/tbx_breakout.h"
+#include "../../toybox_b200/csrc/tbx_space_invaders.h"
+#include "../../toybox_b200/csrc/tbx_amidar.h"
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+using tbxjson::Value;
+
+static const uint32_t BANK[TBX_BANK_WORDS] = TBX_BANK_INIT;
+static thread_local std::string g_err;
+
+struct Emu {
+  int game;
+  const tbx::GameInfo *info;
+  tbx::Config cfg;
+  std::vector<BrkTable> brk_tables;
+  std::vector<AmiTable> ami_tables;
+  std::vector<uint32_t> rec;
+  TbxAcc acc() { TbxAcc S; S.p = rec.data(); S.stride = 1; return S; }
+};
+template <class TT> static int intern(std::vector<TT> &v, const TT &t) {
+  for (size_t i = 0; i < v.size(); i++) if (memcmp(&v[i], &t, sizeof t) == 0) return (int)i;
+  v.push_back(t);
+  return (int)v.size() - 1;
+}
+static void install_default_table(Emu *e) {
+  if (e->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(e->cfg.brk, t); e->cfg.brk.default_tbl = intern(e->brk_tables, t); }
+  else if (e->game == TBX_AMIDAR) { AmiTable t; tbx::ami_default_table(e->cfg.ami, t); e->cfg.ami.default_tbl = intern(e->ami_tables, t); }
+}
+static void new_game(Emu *e) {
+  TbxAcc S = e->acc();
+  if (e->game == TBX_BREAKOUT) brk_new_game(S, e->cfg.brk);
+  else if (e->game == TBX_AMIDAR) ami_new_game(S, e->cfg.ami, e->ami_tables.data());
+  else si_new_game(S, e->cfg.si);
+}
+static char *dup_str(const std::string &s) { char *o = (char *)malloc(s.size() + 1); memcpy(o, s.c_str(), s.size() + 1); return o; }
+
+extern "C" {
+
+const char *emu_last_error(void) { return g_err.c_str(); }
+void emu_free_str(char *s) { free(s); }
+
+Emu *emu_create(const char *game, const char *cfg_json) {
+  int g = tbx::game_from_name(game);
+  if (g < 0) { g_err = "unknown game"; return 0; }
+  Emu *e = new Emu();
+  e->game = g; e->info = tbx::game_info(g);
+  try {
+    tbx::default_config(g, e->cfg);
+    if (cfg_json) tbx::config_from_json(e->cfg, tbxjson::parse(cfg_json));
+    install_default_table(e);
+  } catch (const std::exception &ex) { g_err = ex.what(); delete e; return 0; }
+  e->rec.assign(e->info->rec_words, 0);
+  const uint64_t *rand = g == TBX_BREAKOUT ? e->cfg.brk.rand : g == TBX_AMIDAR ? e->cfg.ami.rand : e->cfg.si.rand;
+  TbxAcc S = e->acc();
+  S.st64(TBX_HW(sim_rand), rand[0]); S.st64(TBX_HW(sim_rand) + 2, rand[1]);
+  for (int k = 0; k < e->info->new_games_at_ctor; k++) new_game(e);
+  return e;
+}
+void emu_destroy(Emu *e) { delete e; }
+int emu_rec_words(Emu *e) { return e->info->rec_words; }
+uint32_t *emu_record(Emu *e) { return e->rec.data(); }
+void emu_seed(Emu *e, uint32_t seed) {
+  TbxRng g; tbx_rng_seed(g, seed);
+  TbxAcc S = e->acc();
+  S.st64(TBX_HW(sim_rand), g.s0); S.st64(TBX_HW(sim_rand) + 2, g.s1);
+}
+void emu_new_game(Emu *e) { new_game(e); }
+
+/* the same sequence step_kernel runs for one env; returns -1 for an invalid ALE id */
+int emu_step(Emu *e, int ale_action, int input_mask, int auto_reset, int32_t *out4) {
+  TbxAcc S = e->acc();
+  int in = input_mask >= 0 ? input_mask : tbx_ale_action_to_input(ale_action);
+  int lives_before = S.ldi(TBX_HW(lives));
+  if (in >= 0) {
+    if (e->game == TBX_BREAKOUT) brk_step(S, e->cfg.brk, e->brk_tables.data(), in);
+    else if (e->game == TBX_AMIDAR) ami_step(S, e->cfg.ami, e->ami_tables.data(), in);
+    else si_step(S, e->cfg.si, in);
+  }
+  TbxStepOut o = tbx_bookkeep(S, lives_before);
+  if (out4) { out4[0] = o.reward; out4[1] = o.done; out4[2] = o.score; out4[3] = o.lives; }
+  if (o.done && auto_reset) new_game(e);
+  return in < 0 ? -1 : 0;
+}
+
+static TbxPrim get_prim(Emu *e, int slot) {
+  if (e->game == TBX_BREAKOUT) return brk_prim(e->rec.data(), e->cfg.brk, e->brk_tables.data(), slot);
+  if (e->game == TBX_AMIDAR) return ami_prim(e->rec.data(), e->cfg.ami, e->ami_tables.data(), slot);
+  return si_prim(e->rec.data(), slot);
+}
+/* mode: 0 rgba 1 rgb 2 gray 3 gray + INTER_AREA to out_w x out_h */
+int emu_render(Emu *e, int mode, int out_w, int out_h, uint8_t *out) {
+  const int W = e->info->width, H = e->info->height;
+  uint32_t clearv = e->game == TBX_BREAKOUT ? e->cfg.brk.bg_color : e->game == TBX_AMIDAR ? e->cfg.ami.bg_color : SI_COLOR_BLACK;
+  std::vector<uint32_t> canvas((size_t)W * H, clearv);
+  for (int s = 0; s < e->info->n_slots; s++) {
+    TbxPrim p = get_prim(e, s);
+    if (p.h <= 0) continue;
+    for (int y = p.y < 0 ? 0 : p.y; y < p.y + p.h && y < H; y++)
+      for (int x = p.x < 0 ? 0 : p.x; x < p.x + p.w && x < W; x++)
+        if (tbx_prim_covers(p, BANK, e->rec.data(), x, y)) canvas[(size_t)y * W + x] = p.color;
+  }
+  if (mode == 0) { memcpy(out, canvas.data(), (size_t)W * H * 4); return 0; }
+  if (mode == 1) { for (int i = 0; i < W * H; i++) { out[3 * i] = canvas[i] & 255; out[3 * i + 1] = (canvas[i] >> 8) & 255; out[3 * i + 2] = (canvas[i] >> 16) & 255; } return 0; }
+  std::vector<uint8_t> gray((size_t)W * H);
+  for (int i = 0; i < W * H; i++) gray[i] = (uint8_t)tbx_luma(canvas[i]);
+  if (mode == 2) { memcpy(out, gray.data(), gray.size()); return 0; }
+  tbx::ResizeTab rs;
+  try { tbx::build_resize(W, H, out_w, out_h, rs); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  std::vector<float> buf((size_t)H * out_w);
+  for (int y = 0; y < H; y++) for (int dx = 0; dx < out_w; dx++) buf[(size_t)y * out_w + dx] = tbx_area_h(gray.data() + (size_t)y * W, rs.x, dx);
+  for (int dy = 0; dy < out_h; dy++) for (int dx = 0; dx < out_w; dx++) out[dy * out_w + dx] = tbx_area_v(buf.data(), out_w, 0, rs.y, dy, dx);
+  return 0;
+}
+
+char *emu_state_to_json(Emu *e) {
+  try {
+    Value v;
+    if (e->game == TBX_BREAKOUT) { const BrkRec &r = *reinterpret_cast<const BrkRec *>(e->rec.data()); v = tbx::brk_state_to_json(r, e->brk_tables[r.hdr.tbl]); }
+    else if (e->game == TBX_AMIDAR) { const AmiRec &r = *reinterpret_cast<const AmiRec *>(e->rec.data()); v = tbx::ami_state_to_json(r, e->ami_tables[r.hdr.tbl]); }
+    else v = tbx::si_state_to_json(*reinterpret_cast<const SiRec *>(e->rec.data()));
+    return dup_str(tbxjson::dump(v));
+  } catch (const std::exception &ex) { g_err = ex.what(); return 0; }
+}
+int emu_state_from_json(Emu *e, const char *json) {
+  std::vector<uint32_t> rec = e->rec;
+  try {
+    Value v = tbxjson::parse(json);
+    if (e->game == TBX_BREAKOUT) { BrkTable t; BrkRec &r = *reinterpret_cast<BrkRec *>(rec.data()); tbx::brk_state_from_json(v, r, t); r.hdr.tbl = intern(e->brk_tables, t); }
+    else if (e->game == TBX_AMIDAR) { AmiTable t; AmiRec &r = *reinterpret_cast<AmiRec *>(rec.data()); tbx::ami_state_from_json(v, r, t); r.hdr.tbl = intern(e->ami_tables, t); }
+    else tbx::si_state_from_json(v, *reinterpret_cast<SiRec *>(rec.data()));
+  } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  e->rec = rec;
+  return 0;
+}
+char *emu_config_to_json(Emu *e) { return dup_str(tbxjson::dump(tbx::config_to_json(e->cfg))); }
+int emu_config_from_json(Emu *e, const char *json) {
+  tbx::Config c = e->cfg;
+  try { tbx::config_from_json(c, tbxjson::parse(json)); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  e->cfg = c;
+  install_default_table(e);
+  return 0;
+}
+char *emu_schema_for_state(const char *game) { return dup_str(tbxjson::dump(tbx::schema_for_state(tbx::game_from_name(game)))); }
+char *emu_schema_for_config(const char *game) { return dup_str(tbxjson::dump(tbx::schema_for_config(tbx::game_from_name(game)))); }
+int emu_n_tables(Emu *e) { return (int)(e->game == TBX_BREAKOUT ? e->brk_tables.size() : e->ami_tables.size()); }
+uint32_t emu_action_index(uint64_t seed, uint64_t env, uint64_t t, uint32_t n_legal) { return tbx_action_index(seed, env, t, n_legal); }
+int emu_ale_action_to_input(int a) { return tbx_ale_action_to_input(a); }
+
+} /* extern "C" */

@@ -1,0 +1,175 @@
+"""GPU tier: the CUDA path (through the C ABI) against the CPU oracle on identical seeds and action streams.
+Bit-exact: scalars every frame, frames in every layout and full state JSON at intervals."""
+import numpy as np
+import pytest
+
+from conftest import json_diff
+
+pytestmark = pytest.mark.gpu
+GAMES = ["breakout", "amidar", "space_invaders"]
+ORACLE_MODE = {"rgba": "rgba", "rgb": "rgb", "gray": "gray", "gray84": "gray84"}
+
+
+def actions_for(oracle_mod, game, n, t, seed=0xB200, env0=0):
+    legal = np.asarray(oracle_mod.LEGAL[game], np.int32)
+    return legal[[oracle_mod.action_index(seed, env0 + i, t, len(legal)) for i in range(n)]]
+
+
+def check_frames(pool, ref, n, modes=("rgba", "rgb", "gray", "gray84")):
+    for mode in modes:
+        got = pool.render(obs=mode).cpu().numpy().reshape(n, -1)
+        want = ref.render(ORACLE_MODE[mode]).reshape(n, -1)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (mode, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_initial_state_matches_fixture_lineage(tbx, oracle_mod, game):
+    """A fresh pool is n copies of what a fresh ctoybox.Toybox(game) holds."""
+    n = 5
+    pool = tbx.BatchedToybox(game, n)
+    ref = oracle_mod.OracleBatch(game, n)
+    states = pool.to_state_json()
+    for i in range(n):
+        assert json_diff(states[i], ref.state_json(i)) == []
+    assert json_diff(pool.config_to_json(), oracle_mod.CODEC[game][2](ref.cfg)) == []
+    check_frames(pool, ref, n)
+    pool.close()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_rollout_bit_exact(tbx, oracle_mod, game):
+    """Random-action rollout with auto-reset from per-env seeds: every scalar every frame, frames + JSON at intervals."""
+    n, steps = 96, 1500
+    pool = tbx.BatchedToybox(game, n, seeds=1234)
+    ref = oracle_mod.OracleBatch(game, n, seeds=1234 + np.arange(n))
+    for t in range(steps):
+        acts = actions_for(oracle_mod, game, n, t)
+        pool.apply_ale_action(acts, auto_reset=True)
+        r, d, s, l = ref.step(acts, auto_reset=True)
+        assert np.array_equal(pool.score.cpu().numpy(), s), t
+        assert np.array_equal(pool.lives.cpu().numpy(), l), t
+        assert np.array_equal(pool.reward.cpu().numpy(), r), t
+        assert np.array_equal(pool.done.cpu().numpy().astype(bool), d), t
+        if t % 100 == 0 or t == steps - 1:
+            check_frames(pool, ref, n)
+            for i in (0, n // 2, n - 1):
+                assert json_diff(pool.to_state_json([i])[0], ref.state_json(i)) == [], (t, i)
+    pool.close()
+
+
+def test_breakout_tracking_policy_hits_bricks(tbx, oracle_mod):
+    """A paddle that tracks the ball clears bricks: exercises paddle bounces, brick hits, speed-up, level refill."""
+    n, steps = 32, 6000
+    pool = tbx.BatchedToybox("breakout", n, seeds=99)
+    ref = oracle_mod.OracleBatch("breakout", n, seeds=99 + np.arange(n))
+    for t in range(steps):
+        acts = np.zeros(n, np.int32)
+        for i in range(n):
+            s = ref.states[i]
+            if s.is_dead:
+                acts[i] = 1
+            else:
+                bx = s.balls[0].position.x if s.n_balls else 120.0
+                off = ((i * 7 + t // 50) % 9) - 4          # deliberate aim error so all paddle segments get used
+                acts[i] = 3 if bx + off > s.paddle.position.x + 1 else 4 if bx + off < s.paddle.position.x - 1 else 0
+        pool.apply_ale_action(acts, auto_reset=True)
+        r, d, s_, l = ref.step(acts, auto_reset=True)
+        assert np.array_equal(pool.score.cpu().numpy(), s_), t
+        assert np.array_equal(pool.lives.cpu().numpy(), l), t
+        if t % 500 == 0 or t == steps - 1:
+            check_frames(pool, ref, n, modes=("rgb", "gray84"))
+            for i in (0, n - 1):
+                assert json_diff(pool.to_state_json([i])[0], ref.state_json(i)) == [], (t, i)
+    assert int(pool.score.max()) > 30
+    pool.close()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_json_round_trip_and_intervention(tbx, oracle_mod, game):
+    """write_state_json(to_state_json()) is the identity, and an edited state steps exactly like the oracle's."""
+    n = 8
+    pool = tbx.BatchedToybox(game, n, seeds=7)
+    ref = oracle_mod.OracleBatch(game, n, seeds=7 + np.arange(n))
+    for t in range(150):
+        acts = actions_for(oracle_mod, game, n, t, seed=5)
+        pool.apply_ale_action(acts, auto_reset=True)
+        ref.step(acts, auto_reset=True)
+    before = pool.to_state_json()
+    pool.write_state_json(before)
+    after = pool.to_state_json()
+    for i in range(n):
+        assert json_diff(before[i], after[i]) == []
+    # intervention on env 2: lives and a game-specific field
+    js = before[2]
+    js["lives"] = 1
+    if game == "breakout":
+        for b in js["bricks"][:12]:
+            b["alive"] = False
+        js["bricks"][20]["color"] = {"r": 1, "g": 2, "b": 3, "a": 255}
+        js["balls"].append({"position": {"x": 100.0, "y": 100.0}, "velocity": {"x": 1.0, "y": -2.0}})
+    elif game == "amidar":
+        js["jumps"] = 1
+        js["enemies"] = js["enemies"][:4]
+        js["enemies"][0]["ai"] = {"EnemyRandomMvmt": {"start": {"tx": 0, "ty": 0}, "start_dir": "Right", "dir": "Right"}}
+    else:
+        js["ufo"]["appearance_counter"] = 3
+        js["shields"][0]["data"][0][5]["a"] = 0
+    pool.write_state_json([js], [2])
+    ref.write_state_json(2, js)
+    assert json_diff(pool.to_state_json([2])[0], ref.state_json(2)) == []
+    for t in range(400):
+        acts = actions_for(oracle_mod, game, n, t, seed=6)
+        pool.apply_ale_action(acts, auto_reset=True)
+        r, d, s, l = ref.step(acts, auto_reset=True)
+        assert np.array_equal(pool.score.cpu().numpy(), s), t
+        assert np.array_equal(pool.lives.cpu().numpy(), l), t
+    check_frames(pool, ref, n)
+    for i in range(n):
+        assert json_diff(pool.to_state_json([i])[0], ref.state_json(i)) == [], i
+    pool.close()
+
+
+def test_ragged_batch_sizes_and_invalid_action(tbx, oracle_mod):
+    for n in (1, 7, 33):
+        pool = tbx.BatchedToybox("space_invaders", n, seeds=3)
+        ref = oracle_mod.OracleBatch("space_invaders", n, seeds=3 + np.arange(n))
+        for t in range(200):
+            acts = actions_for(oracle_mod, "space_invaders", n, t)
+            pool.apply_ale_action(acts)
+            ref.step(acts, auto_reset=False)
+        check_frames(pool, ref, n, modes=("gray", "gray84"))
+        pool.close()
+    pool = tbx.BatchedToybox("breakout", 4)
+    pool.apply_ale_action([0, 1, 99, 3])
+    with pytest.raises(ValueError):
+        pool.check()
+    pool.close()
+
+
+def test_step_host_matches_device_path(tbx, oracle_mod):
+    n = 64
+    pool = tbx.BatchedToybox("breakout", n, seeds=11, obs="gray84")
+    ref = oracle_mod.OracleBatch("breakout", n, seeds=11 + np.arange(n))
+    for t in range(120):
+        acts = actions_for(oracle_mod, "breakout", n, t)
+        obs, r, d, info = pool.step_host(acts)
+        ro, do, so, lo = ref.step(acts, auto_reset=True)
+        assert np.array_equal(r.numpy(), ro) and np.array_equal(info["score"].numpy(), so) and np.array_equal(info["lives"].numpy(), lo)
+    assert np.array_equal(obs.numpy().reshape(n, -1), ref.render("gray84").reshape(n, -1))
+    pool.close()
+
+
+def test_episode_stats(tbx, oracle_mod):
+    n = 128
+    pool = tbx.BatchedToybox("space_invaders", n, seeds=21)
+    ref = oracle_mod.OracleBatch("space_invaders", n, seeds=21 + np.arange(n))
+    episodes = 0
+    for t in range(2500):
+        acts = actions_for(oracle_mod, "space_invaders", n, t)
+        pool.apply_ale_action(acts, auto_reset=True)
+        r, d, s, l = ref.step(acts, auto_reset=True)
+        episodes += int(d.sum())
+    stats = pool.episode_stats()
+    assert stats[0] == episodes
+    pool.close()

@@ -1,0 +1,64 @@
+/* tbx_host.h -- host-side (no CUDA) half of the library: default configs, geometry tables, the JSON
+ * codecs for config and state in the reference's schema, JSON-schema export, INTER_AREA tap tables.
+ * Everything here runs once per pool / per intervention, never per frame.
+ */
+#ifndef TBX_HOST_H
+#define TBX_HOST_H
+#include "tbx_records.h"
+#include "tbx_json.h"
+#include <string>
+#include <vector>
+
+namespace tbx {
+
+struct GameInfo {
+  int id;
+  const char *name;
+  int width, height;
+  int n_legal;
+  int legal[18];
+  int rec_words;
+  int n_slots;
+  int new_games_at_ctor; /* fixture lineage */
+};
+const GameInfo *game_info(int game);
+int game_from_name(const char *name); /* -1 if unknown */
+
+/* one pool-level config, whichever game */
+struct Config {
+  int game;
+  BrkCfg brk;
+  SiCfg si;
+  AmiCfg ami;
+};
+void default_config(int game, Config &c);
+void brk_finish_cfg(BrkCfg &c); /* validates and fills the host-evaluated trig tables */
+tbxjson::Value config_to_json(const Config &c);
+void config_from_json(Config &c, const tbxjson::Value &v); /* throws std::runtime_error */
+
+/* geometry tables */
+void brk_default_table(const BrkCfg &c, BrkTable &t);
+void brk_finish_table(BrkTable &t); /* derived fields (x1,y1, ints, bbox, masks, disjoint) from px..color,destructible */
+void ami_default_table(const AmiCfg &c, AmiTable &t);
+void ami_finish_table(AmiTable &t);
+
+/* state records <-> JSON.  `table` is the geometry table the record refers to (to_json) or the table
+ * the JSON describes (from_json; the caller interns it and sets rec.hdr.tbl). */
+tbxjson::Value brk_state_to_json(const BrkRec &r, const BrkTable &t);
+void brk_state_from_json(const tbxjson::Value &v, BrkRec &r, BrkTable &t);
+tbxjson::Value si_state_to_json(const SiRec &r);
+void si_state_from_json(const tbxjson::Value &v, SiRec &r);
+tbxjson::Value ami_state_to_json(const AmiRec &r, const AmiTable &t);
+void ami_state_from_json(const tbxjson::Value &v, AmiRec &r, AmiTable &t);
+
+tbxjson::Value schema_for_state(int game);
+tbxjson::Value schema_for_config(int game);
+
+/* cv2.resize(..., INTER_AREA) tap tables, general (non-integer scale) path
+ * (baselines/baselines/common/atari_wrappers.py:243) */
+typedef TbxResizeAxis ResizeAxis;
+typedef TbxResizeTab ResizeTab;
+void build_resize(int sw, int sh, int dw, int dh, ResizeTab &t); /* throws if the size pair is not on the general path */
+
+} /* namespace tbx */
+#endif

@@ -1,0 +1,572 @@
+/* tbx_pool.cu -- the C ABI of include/toybox_b200.h: pool life cycle, launches, JSON import/export. */
+#include "../../include/toybox_b200.h"
+#include "tbx_kernels.cuh"
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tbxk;
+using tbxjson::Value;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct tbx_pool {
+  int game, n, n_pad, device;
+  const tbx::GameInfo *info;
+  tbx::Config cfg;
+  void *d_cfg;
+  std::vector<BrkTable> brk_tables;
+  std::vector<AmiTable> ami_tables;
+  void *d_tables;
+  int d_tables_n;
+  uint32_t *planes;
+  unsigned long long *d_stats;
+  int *d_bad;
+  int32_t *d_legal;
+  std::map<std::pair<int, int>, tbx::ResizeTab *> d_resize;
+  /* tbx_step_host staging */
+  cudaStream_t hs;
+  int32_t *h_actions_dev, *h_reward_dev, *h_score_dev, *h_lives_dev;
+  uint8_t *h_done_dev, *h_obs_dev;
+  size_t h_obs_cap;
+};
+
+static size_t cfg_bytes(int game) { return game == TBX_BREAKOUT ? sizeof(BrkCfg) : game == TBX_AMIDAR ? sizeof(AmiCfg) : sizeof(SiCfg); }
+static const void *cfg_ptr(const tbx_pool *p) {
+  return p->game == TBX_BREAKOUT ? (const void *)&p->cfg.brk : p->game == TBX_AMIDAR ? (const void *)&p->cfg.ami : (const void *)&p->cfg.si;
+}
+static int blocks(int n, int t) { return (n + t - 1) / t; }
+
+static int upload_cfg(tbx_pool *p) {
+  CK(cudaMemcpy(p->d_cfg, cfg_ptr(p), cfg_bytes(p->game), cudaMemcpyHostToDevice));
+  return TBX_OK;
+}
+static int upload_tables(tbx_pool *p) {
+  size_t bytes = 0;
+  const void *src = 0;
+  int n = 0;
+  if (p->game == TBX_BREAKOUT) { n = (int)p->brk_tables.size(); bytes = n * sizeof(BrkTable); src = p->brk_tables.data(); }
+  else if (p->game == TBX_AMIDAR) { n = (int)p->ami_tables.size(); bytes = n * sizeof(AmiTable); src = p->ami_tables.data(); }
+  if (n == 0) return TBX_OK;
+  if (n == p->d_tables_n) return TBX_OK;
+  CK(cudaDeviceSynchronize());
+  void *d = 0;
+  CK(cudaMalloc(&d, bytes));
+  CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  if (p->d_tables) cudaFree(p->d_tables);
+  p->d_tables = d;
+  p->d_tables_n = n;
+  return TBX_OK;
+}
+/* index of an identical table, appending it if new */
+template <class TT> static int intern(std::vector<TT> &v, const TT &t) {
+  for (size_t i = 0; i < v.size(); i++) if (memcmp(&v[i], &t, sizeof t) == 0) return (int)i;
+  v.push_back(t);
+  return (int)v.size() - 1;
+}
+static void install_default_table(tbx_pool *p) {
+  if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(p->cfg.brk, t); p->cfg.brk.default_tbl = intern(p->brk_tables, t); }
+  else if (p->game == TBX_AMIDAR) { AmiTable t; tbx::ami_default_table(p->cfg.ami, t); p->cfg.ami.default_tbl = intern(p->ami_tables, t); }
+}
+
+template <int GAME> static void launch_new_game(tbx_pool *p, const uint8_t *mask, cudaStream_t s) {
+  new_game_kernel<GAME><<<blocks(p->n, 128), 128, 0, s>>>(p->planes, p->n, p->n_pad, p->d_cfg, p->d_tables, mask);
+}
+static int do_new_game(tbx_pool *p, const uint8_t *mask, cudaStream_t s) {
+  if (p->game == TBX_BREAKOUT) launch_new_game<TBX_BREAKOUT>(p, mask, s);
+  else if (p->game == TBX_AMIDAR) launch_new_game<TBX_AMIDAR>(p, mask, s);
+  else launch_new_game<TBX_SPACE_INVADERS>(p, mask, s);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
+extern "C" {
+
+const char *tbx_last_error(void) { return g_err.c_str(); }
+int tbx_version(void) { return 100; }
+
+int tbx_pool_destroy(tbx_pool *p) {
+  if (!p) return TBX_OK;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal);
+  for (auto &kv : p->d_resize) cudaFree(kv.second);
+  cudaFree(p->h_actions_dev); cudaFree(p->h_reward_dev); cudaFree(p->h_score_dev); cudaFree(p->h_lives_dev); cudaFree(p->h_done_dev); cudaFree(p->h_obs_dev);
+  if (p->hs) cudaStreamDestroy(p->hs);
+  delete p;
+  return TBX_OK;
+}
+
+int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_json, tbx_pool **out) {
+  if (!out) return set_err(TBX_EINVAL, "out is NULL");
+  *out = 0;
+  int g = tbx::game_from_name(game);
+  if (g < 0) return set_err(TBX_EINVAL, std::string("unknown game '") + (game ? game : "(null)") + "'");
+  if (n_envs < 1) return set_err(TBX_EINVAL, "n_envs must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return set_err(TBX_ECUDA, "no CUDA device available: toybox_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return set_err(TBX_EINVAL, "device index out of range");
+  tbx_pool *p = new (std::nothrow) tbx_pool();
+  if (!p) return set_err(TBX_ENOMEM, "out of host memory");
+  p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
+  p->d_cfg = p->d_tables = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
+  p->hs = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
+  int rc = TBX_OK;
+  try {
+    tbx::default_config(g, p->cfg);
+    if (cfg_json) tbx::config_from_json(p->cfg, tbxjson::parse(cfg_json));
+    install_default_table(p);
+  } catch (const std::exception &e) { delete p; return set_err(TBX_EJSON, e.what()); }
+  auto body = [&]() -> int {
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(&p->d_cfg, cfg_bytes(g)));
+    CK(cudaMalloc(&p->planes, (size_t)p->info->rec_words * p->n_pad * sizeof(uint32_t)));
+    CK(cudaMemset(p->planes, 0, (size_t)p->info->rec_words * p->n_pad * sizeof(uint32_t)));
+    CK(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(p->d_stats, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&p->d_bad, sizeof(int)));
+    CK(cudaMemset(p->d_bad, 0, sizeof(int)));
+    CK(cudaMalloc(&p->d_legal, 18 * sizeof(int32_t)));
+    CK(cudaMemcpy(p->d_legal, p->info->legal, 18 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    int r = upload_cfg(p);
+    if (r) return r;
+    r = upload_tables(p);
+    if (r) return r;
+    const uint64_t *rand = g == TBX_BREAKOUT ? p->cfg.brk.rand : g == TBX_AMIDAR ? p->cfg.ami.rand : p->cfg.si.rand;
+    set_sim_rand_kernel<<<blocks(p->n, 256), 256>>>(p->planes, p->n, p->n_pad, rand[0], rand[1]);
+    CK(cudaGetLastError());
+    for (int k = 0; k < p->info->new_games_at_ctor; k++) { r = do_new_game(p, 0, 0); if (r) return r; }
+    CK(cudaDeviceSynchronize());
+    return TBX_OK;
+  };
+  rc = body();
+  if (rc) { std::string keep = g_err; tbx_pool_destroy(p); g_err = keep; return rc; }
+  *out = p;
+  return TBX_OK;
+}
+
+int tbx_frame_width(const tbx_pool *p) { return p ? p->info->width : 0; }
+int tbx_frame_height(const tbx_pool *p) { return p ? p->info->height : 0; }
+int tbx_n_envs(const tbx_pool *p) { return p ? p->n : 0; }
+int tbx_device(const tbx_pool *p) { return p ? p->device : -1; }
+int tbx_legal_actions(const tbx_pool *p, int32_t *out, int cap) {
+  if (!p) return 0;
+  for (int i = 0; i < p->info->n_legal && i < cap; i++) out[i] = p->info->legal[i];
+  return p->info->n_legal;
+}
+size_t tbx_obs_bytes(const tbx_pool *p, int mode, int out_w, int out_h) {
+  if (!p) return 0;
+  size_t px = (size_t)p->info->width * p->info->height;
+  switch (mode) {
+    case TBX_OBS_RGBA: return px * 4;
+    case TBX_OBS_RGB: return px * 3;
+    case TBX_OBS_GRAY: return px;
+    case TBX_OBS_GRAY_AREA:
+      if (out_w < 1 || out_h < 1 || out_w > p->info->width || out_h > p->info->height || out_w > TBX_RS_MAX_DST || out_h > TBX_RS_MAX_DST) return 0;
+      return (size_t)out_w * out_h;
+  }
+  return 0;
+}
+
+int tbx_seed(tbx_pool *p, const uint32_t *seeds, const int32_t *ids, int n) {
+  if (!p || !seeds || n < 0) return set_err(TBX_EINVAL, "bad arguments");
+  if (!ids && n > p->n) return set_err(TBX_EINVAL, "more seeds than envs");
+  if (n == 0) return TBX_OK;
+  if (ids) for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= p->n) return set_err(TBX_EINVAL, "env id out of range");
+  CK(cudaSetDevice(p->device));
+  uint32_t *d_seeds = 0;
+  int32_t *d_ids = 0;
+  CK(cudaMalloc(&d_seeds, n * sizeof(uint32_t)));
+  CK(cudaMemcpy(d_seeds, seeds, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (ids) { CK(cudaMalloc(&d_ids, n * sizeof(int32_t))); CK(cudaMemcpy(d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice)); }
+  seed_kernel<<<blocks(n, 256), 256>>>(p->planes, p->n_pad, d_seeds, d_ids, n);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  cudaFree(d_seeds); cudaFree(d_ids);
+  return TBX_OK;
+}
+
+int tbx_new_game(tbx_pool *p, const uint8_t *mask, void *stream) {
+  if (!p) return set_err(TBX_EINVAL, "pool is NULL");
+  CK(cudaSetDevice(p->device));
+  return do_new_game(p, mask, (cudaStream_t)stream);
+}
+
+static int do_step(tbx_pool *p, const int32_t *actions, const uint8_t *inputs, int auto_reset, int32_t *reward, uint8_t *done,
+                   int32_t *score, int32_t *lives, cudaStream_t s) {
+  StepArgs a;
+  a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
+  a.actions = actions; a.inputs = inputs; a.auto_reset = auto_reset;
+  a.reward = reward; a.done = done; a.score = score; a.lives = lives; a.stats = p->d_stats; a.bad_actions = p->d_bad;
+  if (p->game == TBX_BREAKOUT) step_kernel<TBX_BREAKOUT><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  else if (p->game == TBX_AMIDAR) step_kernel<TBX_AMIDAR><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  else step_kernel<TBX_SPACE_INVADERS><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+int tbx_step(tbx_pool *p, const int32_t *actions, int auto_reset, int32_t *reward, uint8_t *done, int32_t *score, int32_t *lives, void *stream) {
+  if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
+  CK(cudaSetDevice(p->device));
+  return do_step(p, actions, 0, auto_reset, reward, done, score, lives, (cudaStream_t)stream);
+}
+int tbx_step_inputs(tbx_pool *p, const uint8_t *inputs, int auto_reset, int32_t *reward, uint8_t *done, int32_t *score, int32_t *lives, void *stream) {
+  if (!p || !inputs) return set_err(TBX_EINVAL, "pool/inputs is NULL");
+  CK(cudaSetDevice(p->device));
+  return do_step(p, 0, inputs, auto_reset, reward, done, score, lives, (cudaStream_t)stream);
+}
+int tbx_check(tbx_pool *p, void *stream) {
+  if (!p) return set_err(TBX_EINVAL, "pool is NULL");
+  CK(cudaSetDevice(p->device));
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, p->d_bad, sizeof bad, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (bad) {
+    CK(cudaMemsetAsync(p->d_bad, 0, sizeof(int), (cudaStream_t)stream));
+    return set_err(TBX_EACTION, "Expected to apply action, but failed: " + std::to_string(bad) + " invalid ALE action id(s)");
+  }
+  return TBX_OK;
+}
+
+} /* extern "C" */
+
+/* ---- render */
+struct RenderPlan { int band_rows, canvas_rows, smem_prims, smem_canvas, smem_buf, smem_out, smem_total; };
+static int align16(int v) { return (v + 15) & ~15; }
+static void plan_render(const tbx_pool *p, int mode, int out_w, int out_h, const tbx::ResizeTab *host_rs, RenderPlan &pl) {
+  const int W = p->info->width, H = p->info->height;
+  const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
+  const int budget = 44 * 1024;
+  pl.smem_prims = align16(p->info->rec_words * TBX_EPC * 4);
+  pl.smem_canvas = pl.smem_prims + align16(p->info->n_slots * (int)sizeof(TbxPrim));
+  if (mode != TBX_OBS_GRAY_AREA) {
+    int max_rows = budget / (W * pix);
+    if (max_rows < 1) max_rows = 1;
+    int nb = (H + max_rows - 1) / max_rows;
+    pl.band_rows = (H + nb - 1) / nb;
+    pl.canvas_rows = pl.band_rows;
+    pl.smem_buf = pl.smem_out = pl.smem_canvas + align16(pl.canvas_rows * W * pix);
+    pl.smem_total = pl.smem_buf;
+    return;
+  }
+  const tbx::ResizeAxis &ay = host_rs->y;
+  for (int nb = 1;; nb++) {
+    int br = (out_h + nb - 1) / nb, rows = 0;
+    for (int d0 = 0; d0 < out_h; d0 += br) {
+      int d1 = d0 + br < out_h ? d0 + br : out_h;
+      int r = ay.si[ay.start[d1] - 1] + 1 - ay.si[ay.start[d0]];
+      if (r > rows) rows = r;
+    }
+    if (rows * W + rows * out_w * 4 <= budget || br == 1) { pl.band_rows = br; pl.canvas_rows = rows; break; }
+  }
+  pl.smem_buf = pl.smem_canvas + align16(pl.canvas_rows * W);
+  pl.smem_out = pl.smem_buf + align16(pl.canvas_rows * out_w * 4);
+  pl.smem_total = pl.smem_out + align16(out_w * out_h);
+}
+
+template <int GAME, int MODE> static int launch_render(const RenderArgs &a, int smem, cudaStream_t s) {
+  static int configured = 0; /* per instantiation */
+  if (configured < smem) {
+    CK(cudaFuncSetAttribute(render_kernel<GAME, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 200 * 1024 ? smem : 200 * 1024));
+    configured = 200 * 1024 > smem ? 200 * 1024 : smem;
+  }
+  render_kernel<GAME, MODE><<<blocks(a.n, TBX_EPC), TBX_RENDER_THREADS, smem, s>>>(a);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+template <int GAME> static int launch_render_mode(int mode, const RenderArgs &a, int smem, cudaStream_t s) {
+  switch (mode) {
+    case TBX_OBS_RGBA: return launch_render<GAME, TBX_OBS_RGBA>(a, smem, s);
+    case TBX_OBS_RGB: return launch_render<GAME, TBX_OBS_RGB>(a, smem, s);
+    case TBX_OBS_GRAY: return launch_render<GAME, TBX_OBS_GRAY>(a, smem, s);
+    default: return launch_render<GAME, TBX_OBS_GRAY_AREA>(a, smem, s);
+  }
+}
+
+static int get_resize(tbx_pool *p, int out_w, int out_h, tbx::ResizeTab **dev, tbx::ResizeTab *host) {
+  try { tbx::build_resize(p->info->width, p->info->height, out_w, out_h, *host); }
+  catch (const std::exception &e) { return set_err(TBX_EINVAL, e.what()); }
+  auto key = std::make_pair(out_w, out_h);
+  auto it = p->d_resize.find(key);
+  if (it == p->d_resize.end()) {
+    tbx::ResizeTab *d = 0;
+    CK(cudaMalloc(&d, sizeof(tbx::ResizeTab)));
+    CK(cudaMemcpy(d, host, sizeof(tbx::ResizeTab), cudaMemcpyHostToDevice));
+    it = p->d_resize.insert(std::make_pair(key, d)).first;
+  }
+  *dev = it->second;
+  return TBX_OK;
+}
+
+extern "C" {
+
+int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream) {
+  if (!p || !dst) return set_err(TBX_EINVAL, "pool/dst is NULL");
+  if (((uintptr_t)dst & 15) != 0) return set_err(TBX_EINVAL, "dst must be 16-byte aligned");
+  size_t fb = tbx_obs_bytes(p, mode, out_w, out_h);
+  if (fb == 0) return set_err(TBX_EINVAL, "unsupported observation layout or size");
+  CK(cudaSetDevice(p->device));
+  RenderArgs a;
+  a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
+  a.dst = dst; a.frame_bytes = fb; a.rs = 0; a.out_w = out_w; a.out_h = out_h;
+  tbx::ResizeTab host_rs;
+  if (mode == TBX_OBS_GRAY_AREA) {
+    tbx::ResizeTab *d = 0;
+    int r = get_resize(p, out_w, out_h, &d, &host_rs);
+    if (r) return r;
+    a.rs = d;
+  }
+  RenderPlan pl;
+  plan_render(p, mode, out_w, out_h, &host_rs, pl);
+  a.band_rows = pl.band_rows; a.canvas_rows = pl.canvas_rows;
+  a.smem_prims = pl.smem_prims; a.smem_canvas = pl.smem_canvas; a.smem_buf = pl.smem_buf; a.smem_out = pl.smem_out;
+  if (pl.smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, a, pl.smem_total, s);
+  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, a, pl.smem_total, s);
+  return launch_render_mode<TBX_SPACE_INVADERS>(mode, a, pl.smem_total, s);
+}
+
+int tbx_read_scalars(tbx_pool *p, int32_t *score, int32_t *lives, int32_t *level, void *stream) {
+  if (!p) return set_err(TBX_EINVAL, "pool is NULL");
+  CK(cudaSetDevice(p->device));
+  read_scalars_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, score, lives, level);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
+int tbx_fill_actions(tbx_pool *p, int32_t *actions, uint64_t seed, uint64_t env0, uint64_t t, void *stream) {
+  if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
+  CK(cudaSetDevice(p->device));
+  fill_actions_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(actions, p->n, seed, env0, t, p->d_legal, p->info->n_legal);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
+int tbx_stats_read(tbx_pool *p, int64_t *out, int reset, void *stream) {
+  if (!p || !out) return set_err(TBX_EINVAL, "pool/out is NULL");
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(out, p->d_stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (reset) CK(cudaMemsetAsync(p->d_stats, 0, 4 * sizeof(int64_t), s));
+  return TBX_OK;
+}
+
+int tbx_step_host(tbx_pool *p, const int32_t *actions, int auto_reset, int mode, int out_w, int out_h, uint8_t *obs, int32_t *reward,
+                  uint8_t *done, int32_t *score, int32_t *lives) {
+  if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
+  CK(cudaSetDevice(p->device));
+  const size_t n = (size_t)p->n;
+  if (!p->hs) {
+    CK(cudaStreamCreateWithFlags(&p->hs, cudaStreamNonBlocking));
+    CK(cudaMalloc(&p->h_actions_dev, n * 4)); CK(cudaMalloc(&p->h_reward_dev, n * 4)); CK(cudaMalloc(&p->h_score_dev, n * 4));
+    CK(cudaMalloc(&p->h_lives_dev, n * 4)); CK(cudaMalloc(&p->h_done_dev, n));
+  }
+  size_t fb = 0;
+  if (obs) {
+    fb = tbx_obs_bytes(p, mode, out_w, out_h);
+    if (fb == 0) return set_err(TBX_EINVAL, "unsupported observation layout or size");
+    if (p->h_obs_cap < fb * n) {
+      CK(cudaStreamSynchronize(p->hs));
+      cudaFree(p->h_obs_dev);
+      p->h_obs_dev = 0; p->h_obs_cap = 0;
+      CK(cudaMalloc(&p->h_obs_dev, fb * n));
+      p->h_obs_cap = fb * n;
+    }
+  }
+  CK(cudaMemcpyAsync(p->h_actions_dev, actions, n * 4, cudaMemcpyHostToDevice, p->hs));
+  int r = do_step(p, p->h_actions_dev, 0, auto_reset, p->h_reward_dev, p->h_done_dev, p->h_score_dev, p->h_lives_dev, p->hs);
+  if (r) return r;
+  if (reward) CK(cudaMemcpyAsync(reward, p->h_reward_dev, n * 4, cudaMemcpyDeviceToHost, p->hs));
+  if (done) CK(cudaMemcpyAsync(done, p->h_done_dev, n, cudaMemcpyDeviceToHost, p->hs));
+  if (score) CK(cudaMemcpyAsync(score, p->h_score_dev, n * 4, cudaMemcpyDeviceToHost, p->hs));
+  if (lives) CK(cudaMemcpyAsync(lives, p->h_lives_dev, n * 4, cudaMemcpyDeviceToHost, p->hs));
+  if (obs) {
+    r = tbx_render(p, p->h_obs_dev, mode, out_w, out_h, p->hs);
+    if (r) return r;
+    CK(cudaMemcpyAsync(obs, p->h_obs_dev, fb * n, cudaMemcpyDeviceToHost, p->hs));
+  }
+  CK(cudaStreamSynchronize(p->hs));
+  int bad = 0;
+  CK(cudaMemcpy(&bad, p->d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+  if (bad) { cudaMemset(p->d_bad, 0, sizeof(int)); return set_err(TBX_EACTION, "Expected to apply action, but failed: invalid ALE action id"); }
+  return TBX_OK;
+}
+
+/* ---- JSON */
+static char *dup_str(const std::string &s) {
+  char *out = (char *)malloc(s.size() + 1);
+  if (out) memcpy(out, s.c_str(), s.size() + 1);
+  return out;
+}
+void tbx_free_str(char *s) { free(s); }
+
+static int fetch_records(tbx_pool *p, const int32_t *ids, int n, std::vector<uint32_t> &recs) {
+  const int rw = p->info->rec_words;
+  for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= p->n) return set_err(TBX_EINVAL, "env id out of range");
+  recs.resize((size_t)n * rw);
+  int32_t *d_ids = 0;
+  uint32_t *d_recs = 0;
+  CK(cudaSetDevice(p->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMalloc(&d_ids, n * sizeof(int32_t)));
+  CK(cudaMalloc(&d_recs, recs.size() * 4));
+  CK(cudaMemcpy(d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  gather_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, d_ids, n, rw, d_recs);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(recs.data(), d_recs, recs.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_ids); cudaFree(d_recs);
+  return TBX_OK;
+}
+static int store_records(tbx_pool *p, const int32_t *ids, int n, const std::vector<uint32_t> &recs) {
+  const int rw = p->info->rec_words;
+  int32_t *d_ids = 0;
+  uint32_t *d_recs = 0;
+  CK(cudaMalloc(&d_ids, n * sizeof(int32_t)));
+  CK(cudaMalloc(&d_recs, recs.size() * 4));
+  CK(cudaMemcpy(d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_recs, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice));
+  scatter_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, d_ids, n, rw, d_recs);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  cudaFree(d_ids); cudaFree(d_recs);
+  return TBX_OK;
+}
+
+int tbx_state_to_json(tbx_pool *p, const int32_t *ids, int n, char **out) {
+  if (!p || !ids || !out || n < 0) return set_err(TBX_EINVAL, "bad arguments");
+  for (int i = 0; i < n; i++) out[i] = 0;
+  if (n == 0) return TBX_OK;
+  std::vector<uint32_t> recs;
+  int r = fetch_records(p, ids, n, recs);
+  if (r) return r;
+  const int rw = p->info->rec_words;
+  try {
+    for (int i = 0; i < n; i++) {
+      const uint32_t *R = recs.data() + (size_t)i * rw;
+      Value v;
+      if (p->game == TBX_BREAKOUT) {
+        const BrkRec &rec = *reinterpret_cast<const BrkRec *>(R);
+        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->brk_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
+        v = tbx::brk_state_to_json(rec, p->brk_tables[rec.hdr.tbl]);
+      } else if (p->game == TBX_AMIDAR) {
+        const AmiRec &rec = *reinterpret_cast<const AmiRec *>(R);
+        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->ami_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
+        v = tbx::ami_state_to_json(rec, p->ami_tables[rec.hdr.tbl]);
+      } else v = tbx::si_state_to_json(*reinterpret_cast<const SiRec *>(R));
+      out[i] = dup_str(tbxjson::dump(v));
+      if (!out[i]) return set_err(TBX_ENOMEM, "out of host memory");
+    }
+  } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  return TBX_OK;
+}
+
+int tbx_state_from_json(tbx_pool *p, const int32_t *ids, int n, const char *const *json) {
+  if (!p || !ids || !json || n < 0) return set_err(TBX_EINVAL, "bad arguments");
+  if (n == 0) return TBX_OK;
+  std::vector<uint32_t> recs;
+  int r = fetch_records(p, ids, n, recs); /* keeps the fields JSON does not carry (simulator rand, episode counters) */
+  if (r) return r;
+  const int rw = p->info->rec_words;
+  /* parse everything before touching the pool so a bad document leaves it unchanged */
+  std::vector<BrkTable> new_brk;
+  std::vector<AmiTable> new_ami;
+  try {
+    for (int i = 0; i < n; i++) {
+      uint32_t *R = recs.data() + (size_t)i * rw;
+      Value v = tbxjson::parse(json[i]);
+      if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_state_from_json(v, *reinterpret_cast<BrkRec *>(R), t); new_brk.push_back(t); }
+      else if (p->game == TBX_AMIDAR) { AmiTable t; tbx::ami_state_from_json(v, *reinterpret_cast<AmiRec *>(R), t); new_ami.push_back(t); }
+      else tbx::si_state_from_json(v, *reinterpret_cast<SiRec *>(R));
+    }
+  } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  for (int i = 0; i < n; i++) {
+    uint32_t *R = recs.data() + (size_t)i * rw;
+    if (p->game == TBX_BREAKOUT) reinterpret_cast<BrkRec *>(R)->hdr.tbl = intern(p->brk_tables, new_brk[i]);
+    else if (p->game == TBX_AMIDAR) reinterpret_cast<AmiRec *>(R)->hdr.tbl = intern(p->ami_tables, new_ami[i]);
+  }
+  r = upload_tables(p);
+  if (r) return r;
+  return store_records(p, ids, n, recs);
+}
+
+int tbx_config_to_json(tbx_pool *p, char **out) {
+  if (!p || !out) return set_err(TBX_EINVAL, "bad arguments");
+  try { *out = dup_str(tbxjson::dump(tbx::config_to_json(p->cfg))); } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
+}
+int tbx_config_from_json(tbx_pool *p, const char *json) {
+  if (!p || !json) return set_err(TBX_EINVAL, "bad arguments");
+  tbx::Config c = p->cfg;
+  try { tbx::config_from_json(c, tbxjson::parse(json)); } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  CK(cudaSetDevice(p->device));
+  CK(cudaDeviceSynchronize());
+  p->cfg = c;
+  install_default_table(p);
+  int r = upload_tables(p);
+  if (r) return r;
+  return upload_cfg(p);
+}
+int tbx_schema_for_state(const char *game, char **out) {
+  int g = tbx::game_from_name(game);
+  if (g < 0 || !out) return set_err(TBX_EINVAL, "unknown game");
+  *out = dup_str(tbxjson::dump(tbx::schema_for_state(g)));
+  return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
+}
+int tbx_schema_for_config(const char *game, char **out) {
+  int g = tbx::game_from_name(game);
+  if (g < 0 || !out) return set_err(TBX_EINVAL, "unknown game");
+  try { *out = dup_str(tbxjson::dump(tbx::schema_for_config(g))); } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
+}
+int tbx_query_json(tbx_pool *p, int env, const char *query, const char *args_json, char **out) {
+  if (!p || !query || !out) return set_err(TBX_EINVAL, "bad arguments");
+  *out = 0;
+  if (env < 0 || env >= p->n) return set_err(TBX_EINVAL, "env id out of range");
+  try {
+    Value args = tbxjson::parse(args_json ? args_json : "null");
+    std::string q(query);
+    Value res;
+    if (p->game == TBX_AMIDAR && q == "tile_to_world") {
+      res = Value::array();
+      res.push(Value::integer((int64_t)args.at("tx").as_i32() * AMI_TW)).push(Value::integer((int64_t)args.at("ty").as_i32() * AMI_TH));
+    } else if (p->game == TBX_AMIDAR && q == "world_to_tile") {
+      res = Value::array();
+      res.push(Value::integer(ami_floordiv(args.at("x").as_i32(), AMI_TW))).push(Value::integer(ami_floordiv(args.at("y").as_i32(), AMI_TH)));
+    } else if (p->game == TBX_BREAKOUT && (q == "bricks_remaining" || q == "count_channels" || q == "channels")) {
+      std::vector<uint32_t> recs;
+      int32_t id = env;
+      int r = fetch_records(p, &id, 1, recs);
+      if (r) return r;
+      const BrkRec &rec = *reinterpret_cast<const BrkRec *>(recs.data());
+      const BrkTable &t = p->brk_tables[rec.hdr.tbl];
+      if (q == "bricks_remaining") {
+        int c = 0;
+        for (int i = 0; i < t.n_bricks; i++) c += (rec.alive[i >> 5] >> (i & 31)) & 1u;
+        res = Value::integer(c);
+      } else {
+        /* a channel is a brick column with no alive brick left */
+        res = Value::array();
+        int count = 0;
+        for (int col = 0; col < 64; col++) {
+          bool any = false, open = true;
+          for (int i = 0; i < t.n_bricks; i++) if (t.col[i] == col) { any = true; if ((rec.alive[i >> 5] >> (i & 31)) & 1u) open = false; }
+          if (any && open) { count++; res.push(Value::integer(col)); }
+        }
+        if (q == "count_channels") res = Value::integer(count);
+      }
+    } else return set_err(TBX_EINVAL, "unknown query '" + q + "'");
+    *out = dup_str(tbxjson::dump(res));
+  } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
+}
+
+} /* extern "C" */
