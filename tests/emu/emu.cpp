@@ -153,6 +153,12 @@ int emu_config_from_json(Emu *e, const char *json) {
   install_default_table(e);
   return 0;
 }
+char *emu_query_json(Emu *e, const char *query, const char *args_json) {
+  try {
+    const BrkTable *brk = e->game == TBX_BREAKOUT ? &e->brk_tables[reinterpret_cast<const BrkRec *>(e->rec.data())->hdr.tbl] : 0;
+    return dup_str(tbxjson::dump(tbx::query_json(e->game, e->rec.data(), brk, query, tbxjson::parse(args_json ? args_json : "null"))));
+  } catch (const std::exception &ex) { g_err = ex.what(); return 0; }
+}
 char *emu_schema_for_state(const char *game) { return dup_str(tbxjson::dump(tbx::schema_for_state(tbx::game_from_name(game)))); }
 char *emu_schema_for_config(const char *game) { return dup_str(tbxjson::dump(tbx::schema_for_config(tbx::game_from_name(game)))); }
 int emu_n_tables(Emu *e) { return (int)(e->game == TBX_BREAKOUT ? e->brk_tables.size() : e->ami_tables.size()); }

@@ -671,6 +671,41 @@ void ami_state_from_json(const Value &v, AmiRec &r, AmiTable &t) {
   ami_finish_table(t);
 }
 
+/* ------------------------------------------------------------------ queries */
+Value query_json(int game, const uint32_t *rec, const BrkTable *brk, const std::string &q, const Value &args) {
+  if (game == TBX_AMIDAR && q == "tile_to_world") {
+    Value res = Value::array();
+    res.push(Value::integer((int64_t)args.at("tx").as_i32() * AMI_TW)).push(Value::integer((int64_t)args.at("ty").as_i32() * AMI_TH));
+    return res;
+  }
+  if (game == TBX_AMIDAR && q == "world_to_tile") {
+    Value res = Value::array();
+    res.push(Value::integer(ami_floordiv(args.at("x").as_i32(), AMI_TW))).push(Value::integer(ami_floordiv(args.at("y").as_i32(), AMI_TH)));
+    return res;
+  }
+  if (game == TBX_BREAKOUT && brk && (q == "bricks_remaining" || q == "count_channels" || q == "channels")) {
+    const BrkRec &r = *reinterpret_cast<const BrkRec *>(rec);
+    const BrkTable &t = *brk;
+    if (q == "bricks_remaining") {
+      int c = 0;
+      for (int i = 0; i < t.n_bricks; i++) c += (r.alive[i >> 5] >> (i & 31)) & 1u;
+      return Value::integer(c);
+    }
+    /* a channel is a brick column with no alive brick left */
+    Value cols = Value::array();
+    int count = 0;
+    for (int col = 0; col < 64; col++) {
+      bool any = false, open = true;
+      for (int i = 0; i < t.n_bricks; i++)
+        if (t.col[i] == col) { any = true; if ((r.alive[i >> 5] >> (i & 31)) & 1u) open = false; }
+      if (any && open) { count++; cols.push(Value::integer(col)); }
+    }
+    return q == "count_channels" ? Value::integer(count) : cols;
+  }
+  fail("unknown query '" + q + "'");
+  return Value();
+}
+
 /* ------------------------------------------------------------------ JSON schema (draft-07 flavoured, what
  * toybox/interventions/core.py:18-20 and the classes' `expected_keys` read: top-level `required` and
  * per-property `type`/`format`) */

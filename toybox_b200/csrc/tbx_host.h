@@ -51,6 +51,11 @@ void si_state_from_json(const tbxjson::Value &v, SiRec &r);
 tbxjson::Value ami_state_to_json(const AmiRec &r, const AmiTable &t);
 void ami_state_from_json(const tbxjson::Value &v, AmiRec &r, AmiTable &t);
 
+/* Toybox.query_state_json(query, args) (toybox/interventions/amidar.py:508-518): amidar tile_to_world /
+ * world_to_tile; breakout bricks_remaining / count_channels / channels.  `rec` is the env's record, `brk` its
+ * brick table (breakout only).  Throws on an unknown query. */
+tbxjson::Value query_json(int game, const uint32_t *rec, const BrkTable *brk, const std::string &query, const tbxjson::Value &args);
+
 tbxjson::Value schema_for_state(int game);
 tbxjson::Value schema_for_config(int game);
 

@@ -534,36 +534,17 @@ int tbx_query_json(tbx_pool *p, int env, const char *query, const char *args_jso
   try {
     Value args = tbxjson::parse(args_json ? args_json : "null");
     std::string q(query);
-    Value res;
-    if (p->game == TBX_AMIDAR && q == "tile_to_world") {
-      res = Value::array();
-      res.push(Value::integer((int64_t)args.at("tx").as_i32() * AMI_TW)).push(Value::integer((int64_t)args.at("ty").as_i32() * AMI_TH));
-    } else if (p->game == TBX_AMIDAR && q == "world_to_tile") {
-      res = Value::array();
-      res.push(Value::integer(ami_floordiv(args.at("x").as_i32(), AMI_TW))).push(Value::integer(ami_floordiv(args.at("y").as_i32(), AMI_TH)));
-    } else if (p->game == TBX_BREAKOUT && (q == "bricks_remaining" || q == "count_channels" || q == "channels")) {
-      std::vector<uint32_t> recs;
+    std::vector<uint32_t> recs;
+    const BrkTable *brk = 0;
+    if (p->game == TBX_BREAKOUT) {
       int32_t id = env;
       int r = fetch_records(p, &id, 1, recs);
       if (r) return r;
-      const BrkRec &rec = *reinterpret_cast<const BrkRec *>(recs.data());
-      const BrkTable &t = p->brk_tables[rec.hdr.tbl];
-      if (q == "bricks_remaining") {
-        int c = 0;
-        for (int i = 0; i < t.n_bricks; i++) c += (rec.alive[i >> 5] >> (i & 31)) & 1u;
-        res = Value::integer(c);
-      } else {
-        /* a channel is a brick column with no alive brick left */
-        res = Value::array();
-        int count = 0;
-        for (int col = 0; col < 64; col++) {
-          bool any = false, open = true;
-          for (int i = 0; i < t.n_bricks; i++) if (t.col[i] == col) { any = true; if ((rec.alive[i >> 5] >> (i & 31)) & 1u) open = false; }
-          if (any && open) { count++; res.push(Value::integer(col)); }
-        }
-        if (q == "count_channels") res = Value::integer(count);
-      }
-    } else return set_err(TBX_EINVAL, "unknown query '" + q + "'");
+      int tbl = reinterpret_cast<const BrkRec *>(recs.data())->hdr.tbl;
+      if (tbl < 0 || tbl >= (int)p->brk_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
+      brk = &p->brk_tables[tbl];
+    }
+    Value res = tbx::query_json(p->game, recs.data(), brk, q, args);
     *out = dup_str(tbxjson::dump(res));
   } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
   return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
