@@ -125,6 +125,69 @@ int emu_render(Emu *e, int mode, int out_w, int out_h, uint8_t *out) {
   return 0;
 }
 
+/* The fused kernel's INTER_AREA algorithm, step for step on the host: static base frame + its pre-computed
+ * down-sample, dynamic groups painted over the base, dirty rectangles (group bounding boxes / per-primitive
+ * boxes of the in-order group), and only the output pixels fed by a dirty rectangle recomputed with the
+ * zero-padded fixed-tap arithmetic of TbxAreaPlan.  Must equal emu_render(mode 3). */
+int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
+  const int W = e->info->width, H = e->info->height;
+  tbx::ResizeTab rs;
+  TbxAreaPlan pl;
+  try { tbx::build_resize(W, H, out_w, out_h, rs); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  if (!tbx::build_area_plan(rs, pl)) { g_err = "size pair outside the fused kernel's limits"; return -1; }
+  std::vector<uint32_t> base((size_t)W * H);
+  tbx::build_base_frame(e->cfg, base.data());
+  std::vector<uint8_t> canvas((size_t)W * H + 16, 0);
+  tbx::frame_to_gray(base.data(), W * H, canvas.data());
+  tbx::area_resize(canvas.data(), rs, out);
+  struct Rect { int x0, y0, x1, y1; };
+  std::vector<Rect> rects;
+  const int ng = e->game == TBX_BREAKOUT ? BRK_N_GROUPS : e->game == TBX_AMIDAR ? AMI_N_GROUPS : SI_N_GROUPS;
+  int covered = tbx::n_static_slots(e->game);
+  for (int g = 0; g < ng; g++) {
+    int gb, ge, mode;
+    if (e->game == TBX_BREAKOUT) brk_group(g, e->rec.data(), e->brk_tables.data(), gb, ge, mode);
+    else if (e->game == TBX_AMIDAR) ami_group(g, gb, ge, mode);
+    else si_group(g, gb, ge, mode);
+    if (gb != covered) { g_err = "groups do not tile the dynamic slots"; return -1; }
+    covered = ge;
+    Rect box = {32767, 32767, -1, -1};
+    const bool per_prim = mode == TBX_GROUP_SERIAL && ge - gb <= 32;
+    for (int s = gb; s < ge; s++) {
+      TbxPrim p = get_prim(e, s);
+      Rect c = {p.x < 0 ? 0 : p.x, p.y < 0 ? 0 : p.y, p.x + p.w > W ? W : p.x + p.w, p.y + p.h > H ? H : p.y + p.h};
+      if (p.h <= 0 || c.x0 >= c.x1 || c.y0 >= c.y1) continue;
+      uint8_t val = (uint8_t)tbx_luma(p.color);
+      for (int y = c.y0; y < c.y1; y++)
+        for (int x = c.x0; x < c.x1; x++)
+          if (tbx_prim_covers(p, BANK, e->rec.data(), x, y)) canvas[(size_t)y * W + x] = val;
+      if (per_prim) rects.push_back(c);
+      else { if (c.x0 < box.x0) box.x0 = c.x0; if (c.y0 < box.y0) box.y0 = c.y0; if (c.x1 > box.x1) box.x1 = c.x1; if (c.y1 > box.y1) box.y1 = c.y1; }
+    }
+    if (!per_prim && box.x1 > box.x0) rects.push_back(box);
+  }
+  if (covered != e->info->n_slots) { g_err = "groups do not tile the dynamic slots"; return -1; }
+  for (size_t r = 0; r < rects.size(); r++) {
+    const Rect &rc = rects[r];
+    const int dx0 = pl.xdlo[rc.x0], dx1 = pl.xdhi[rc.x1 - 1], dy0 = pl.ydlo[rc.y0], dy1 = pl.ydhi[rc.y1 - 1];
+    for (int dy = dy0; dy <= dy1; dy++)
+      for (int dx = dx0; dx <= dx1; dx++) {
+        const uint8_t *src = canvas.data() + (size_t)pl.ys0[dy] * W + pl.xs0[dx];
+        float v = 0.0f;
+        for (int k = 0; k < pl.yn[dy]; k++) {
+          const uint8_t *row = src + (size_t)k * W;
+          float h = tbx_fmul((float)row[0], pl.xalpha[0][dx]);
+          for (int t = 1; t < pl.tx; t++) h = tbx_fadd(h, tbx_fmul((float)row[t], pl.xalpha[t][dx]));
+          const float bh = tbx_fmul(pl.yalpha[k][dy], h);
+          v = k == 0 ? bh : tbx_fadd(v, bh);
+        }
+        const int iv = tbx_f2i_rn(v);
+        out[dy * out_w + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+      }
+  }
+  return 0;
+}
+
 char *emu_state_to_json(Emu *e) {
   try {
     Value v;

@@ -99,6 +99,14 @@ class Emu:
             raise ValueError(self.L.emu_last_error().decode())
         return out
 
+    def render_fast(self, out_w=84, out_h=84):
+        """The fused kernel's INTER_AREA algorithm (base frame + dirty rectangles), emulated on the host."""
+        out = np.empty((out_h, out_w), np.uint8)
+        self.L.emu_render_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        if self.L.emu_render_fast(self.h, out_w, out_h, out.ctypes.data_as(C.c_void_p)) != 0:
+            raise ValueError(self.L.emu_last_error().decode())
+        return out
+
     def state_json(self):
         return json.loads(_take(self.L.emu_state_to_json(self.h)))
 

@@ -31,6 +31,15 @@
 #define AMI_SLOT_LIVES (AMI_SLOT_SCORE + TBX_MAX_DIGITS)
 #define AMI_SLOT_JUMPS (AMI_SLOT_LIVES + TBX_MAX_DIGITS)
 #define AMI_N_SLOTS (AMI_SLOT_JUMPS + TBX_MAX_DIGITS)
+#define AMI_N_STATIC 0
+#define AMI_N_GROUPS 4
+/* tiles (a grid) | painted box interiors (one colour) | enemies (one colour) | player, score, lives, jumps (in order) */
+TBX_HD void ami_group(int g, int &b, int &e, int &mode) {
+  if (g == 0) { b = AMI_SLOT_TILES; e = AMI_SLOT_BOXES; mode = TBX_GROUP_PARALLEL; }
+  else if (g == 1) { b = AMI_SLOT_BOXES; e = AMI_SLOT_ENEMIES; mode = TBX_GROUP_PARALLEL; }
+  else if (g == 2) { b = AMI_SLOT_ENEMIES; e = AMI_SLOT_PLAYER; mode = TBX_GROUP_PARALLEL; }
+  else { b = AMI_SLOT_PLAYER; e = AMI_N_SLOTS; mode = TBX_GROUP_SERIAL; }
+}
 
 TBX_HD int ami_floordiv(int a, int b) { int q = a / b; if ((a % b) != 0 && ((a < 0) != (b < 0))) q--; return q; }
 TBX_HD int ami_dx(int d) { return d == TBX_DIR_LEFT ? -1 : d == TBX_DIR_RIGHT ? 1 : 0; }

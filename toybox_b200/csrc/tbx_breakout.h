@@ -27,6 +27,14 @@
 #define BRK_SLOT_PADDLE (BRK_SLOT_BRICKS + TBX_BRK_MAX_BRICKS)
 #define BRK_SLOT_BALLS (BRK_SLOT_PADDLE + 1)                 /* TBX_BRK_MAX_BALLS */
 #define BRK_N_SLOTS (BRK_SLOT_BALLS + TBX_BRK_MAX_BALLS)
+#define BRK_N_STATIC 3 /* leading slots that depend on the config only */
+#define BRK_N_GROUPS 3
+/* HUD digits (one colour) | bricks (parallel iff the table's rectangles are disjoint) | paddle, balls (in order) */
+TBX_HD void brk_group(int g, const uint32_t *R, const BrkTable *tables, int &b, int &e, int &mode) {
+  if (g == 0) { b = BRK_SLOT_SCORE; e = BRK_SLOT_BRICKS; mode = TBX_GROUP_PARALLEL; }
+  else if (g == 1) { b = BRK_SLOT_BRICKS; e = BRK_SLOT_PADDLE; mode = tables[(int32_t)R[TBX_W(TbxHdr, tbl)]].disjoint ? TBX_GROUP_PARALLEL : TBX_GROUP_SERIAL; }
+  else { b = BRK_SLOT_PADDLE; e = BRK_N_SLOTS; mode = TBX_GROUP_SERIAL; }
+}
 
 TBX_HD double brk_vmag(double vx, double vy) { return tbx_dsqrt(tbx_dadd(tbx_dmul(vx, vx), tbx_dmul(vy, vy))); }
 

@@ -801,4 +801,56 @@ void build_resize(int sw, int sh, int dw, int dh, ResizeTab &t) {
   build_axis(sh, dh, t.y);
 }
 
+bool build_area_plan(const ResizeTab &t, TbxAreaPlan &pl) {
+  memset(&pl, 0, sizeof pl);
+  const ResizeAxis *ax[2] = {&t.x, &t.y};
+  if (t.x.dsize > TBX_AREA_MAX_DST || t.y.dsize > TBX_AREA_MAX_DST || t.x.ssize > TBX_AREA_MAX_SRC || t.y.ssize > TBX_AREA_MAX_SRC) return false;
+  if (t.x.max_taps > TBX_AREA_MAX_TAPS || t.y.max_taps > TBX_AREA_MAX_TAPS) return false;
+  pl.sw = t.x.ssize; pl.sh = t.y.ssize; pl.dw = t.x.dsize; pl.dh = t.y.dsize; pl.tx = t.x.max_taps; pl.ty = t.y.max_taps;
+  for (int a = 0; a < 2; a++) {
+    const ResizeAxis &A = *ax[a];
+    uint8_t *dlo = a == 0 ? pl.xdlo : pl.ydlo, *dhi = a == 0 ? pl.xdhi : pl.ydhi;
+    for (int s = 0; s < TBX_AREA_MAX_SRC; s++) { dlo[s] = 255; dhi[s] = 0; }
+    for (int d = 0; d < A.dsize; d++) {
+      int k0 = A.start[d], n = A.start[d + 1] - k0;
+      for (int k = 0; k < n; k++) if (A.si[k0 + k] != A.si[k0] + k) return false; /* taps must be consecutive */
+      (a == 0 ? pl.xs0 : pl.ys0)[d] = A.si[k0];
+      if (a == 1) pl.yn[d] = (uint16_t)n;
+      for (int k = 0; k < TBX_AREA_MAX_TAPS; k++) (a == 0 ? pl.xalpha : pl.yalpha)[k][d] = k < n ? A.alpha[k0 + k] : 0.0f;
+      for (int k = 0; k < n; k++) {
+        int si = A.si[k0 + k];
+        if (d < dlo[si]) dlo[si] = (uint8_t)d;
+        if (d > dhi[si]) dhi[si] = (uint8_t)d;
+      }
+    }
+    /* a source index that feeds nothing (cannot happen when down-sampling) inherits its neighbour's range */
+    for (int s = 0; s < A.ssize; s++) if (dlo[s] > dhi[s]) { dlo[s] = s ? dlo[s - 1] : 0; dhi[s] = s ? dhi[s - 1] : 0; }
+  }
+  return true;
+}
+
+int n_static_slots(int game) { return game == TBX_BREAKOUT ? BRK_N_STATIC : game == TBX_AMIDAR ? AMI_N_STATIC : SI_N_STATIC; }
+static const uint32_t HOST_BANK[TBX_BANK_WORDS] = TBX_BANK_INIT;
+void build_base_frame(const Config &c, uint32_t *rgba) {
+  const GameInfo *gi = game_info(c.game);
+  const int W = gi->width, H = gi->height;
+  uint32_t clearv = c.game == TBX_BREAKOUT ? c.brk.bg_color : c.game == TBX_AMIDAR ? c.ami.bg_color : SI_COLOR_BLACK;
+  for (int i = 0; i < W * H; i++) rgba[i] = clearv;
+  std::vector<uint32_t> rec(gi->rec_words, 0); /* static slots never read the record */
+  for (int s = 0; s < n_static_slots(c.game); s++) {
+    TbxPrim p = c.game == TBX_BREAKOUT ? brk_prim(rec.data(), c.brk, 0, s) : c.game == TBX_AMIDAR ? ami_prim(rec.data(), c.ami, 0, s) : si_prim(rec.data(), s);
+    if (p.h <= 0) continue;
+    for (int y = p.y < 0 ? 0 : p.y; y < p.y + p.h && y < H; y++)
+      for (int x = p.x < 0 ? 0 : p.x; x < p.x + p.w && x < W; x++)
+        if (tbx_prim_covers(p, HOST_BANK, rec.data(), x, y)) rgba[(size_t)y * W + x] = p.color;
+  }
+}
+void frame_to_gray(const uint32_t *rgba, int npix, uint8_t *gray) { for (int i = 0; i < npix; i++) gray[i] = (uint8_t)tbx_luma(rgba[i]); }
+void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out) {
+  const int W = t.x.ssize, H = t.y.ssize, dw = t.x.dsize, dh = t.y.dsize;
+  std::vector<float> buf((size_t)H * dw);
+  for (int y = 0; y < H; y++) for (int dx = 0; dx < dw; dx++) buf[(size_t)y * dw + dx] = tbx_area_h(gray + (size_t)y * W, t.x, dx);
+  for (int dy = 0; dy < dh; dy++) for (int dx = 0; dx < dw; dx++) out[dy * dw + dx] = tbx_area_v(buf.data(), dw, 0, t.y, dy, dx);
+}
+
 } /* namespace tbx */

@@ -64,6 +64,16 @@ tbxjson::Value schema_for_config(int game);
 typedef TbxResizeAxis ResizeAxis;
 typedef TbxResizeTab ResizeTab;
 void build_resize(int sw, int sh, int dw, int dh, ResizeTab &t); /* throws if the size pair is not on the general path */
+/* repack for the fused kernel; returns false when the size pair exceeds its limits (the generic kernel handles those) */
+bool build_area_plan(const ResizeTab &t, TbxAreaPlan &plan);
+
+/* Static part of a game's frame: the leading draw-list slots that depend on the config only (Breakout: frame
+ * walls; Space Invaders: ground line; Amidar: none) painted over the clear colour.  rgba: W*H pixels. */
+int n_static_slots(int game);
+void build_base_frame(const Config &c, uint32_t *rgba);
+/* gray bytes of an RGBA frame, and its INTER_AREA down-sample (same arithmetic as the kernels) */
+void frame_to_gray(const uint32_t *rgba, int npix, uint8_t *gray);
+void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out);
 
 } /* namespace tbx */
 #endif

@@ -17,6 +17,9 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out; int dw, dh; };
+static void drop_render_cache(struct tbx_pool *p);
+
 struct tbx_pool {
   int game, n, n_pad, device;
   const tbx::GameInfo *info;
@@ -30,7 +33,11 @@ struct tbx_pool {
   unsigned long long *d_stats;
   int *d_bad;
   int32_t *d_legal;
-  std::map<std::pair<int, int>, tbx::ResizeTab *> d_resize;
+  /* render resources of the current config: static frame (gray, RGBA) and per output size the INTER_AREA plan */
+  uint8_t *d_base_gray, *d_base_rgba;
+  std::vector<uint32_t> h_base_rgba;
+  std::vector<uint8_t> h_base_gray;
+  std::map<std::pair<int, int>, struct AreaRes> area;
   /* tbx_step_host staging */
   cudaStream_t hs;
   int32_t *h_actions_dev, *h_reward_dev, *h_score_dev, *h_lives_dev;
@@ -97,7 +104,7 @@ int tbx_pool_destroy(tbx_pool *p) {
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
   cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal);
-  for (auto &kv : p->d_resize) cudaFree(kv.second);
+  drop_render_cache(p);
   cudaFree(p->h_actions_dev); cudaFree(p->h_reward_dev); cudaFree(p->h_score_dev); cudaFree(p->h_lives_dev); cudaFree(p->h_done_dev); cudaFree(p->h_obs_dev);
   if (p->hs) cudaStreamDestroy(p->hs);
   delete p;
@@ -117,7 +124,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   tbx_pool *p = new (std::nothrow) tbx_pool();
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
-  p->d_cfg = p->d_tables = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
+  p->d_cfg = p->d_tables = 0; p->d_base_gray = p->d_base_rgba = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
   p->hs = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
@@ -238,44 +245,57 @@ int tbx_check(tbx_pool *p, void *stream) {
 } /* extern "C" */
 
 /* ---- render */
-struct RenderPlan { int band_rows, canvas_rows, smem_prims, smem_canvas, smem_buf, smem_out, smem_total; };
-static int align16(int v) { return (v + 15) & ~15; }
-static void plan_render(const tbx_pool *p, int mode, int out_w, int out_h, const tbx::ResizeTab *host_rs, RenderPlan &pl) {
-  const int W = p->info->width, H = p->info->height;
-  const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
-  const int budget = 44 * 1024;
-  pl.smem_prims = align16(p->info->rec_words * TBX_EPC * 4);
-  pl.smem_canvas = pl.smem_prims + align16(p->info->n_slots * (int)sizeof(TbxPrim));
-  if (mode != TBX_OBS_GRAY_AREA) {
-    int max_rows = budget / (W * pix);
-    if (max_rows < 1) max_rows = 1;
-    int nb = (H + max_rows - 1) / max_rows;
-    pl.band_rows = (H + nb - 1) / nb;
-    pl.canvas_rows = pl.band_rows;
-    pl.smem_buf = pl.smem_out = pl.smem_canvas + align16(pl.canvas_rows * W * pix);
-    pl.smem_total = pl.smem_buf;
-    return;
-  }
-  const tbx::ResizeAxis &ay = host_rs->y;
-  for (int nb = 1;; nb++) {
-    int br = (out_h + nb - 1) / nb, rows = 0;
-    for (int d0 = 0; d0 < out_h; d0 += br) {
-      int d1 = d0 + br < out_h ? d0 + br : out_h;
-      int r = ay.si[ay.start[d1] - 1] + 1 - ay.si[ay.start[d0]];
-      if (r > rows) rows = r;
-    }
-    if (rows * W + rows * out_w * 4 <= budget || br == 1) { pl.band_rows = br; pl.canvas_rows = rows; break; }
-  }
-  pl.smem_buf = pl.smem_canvas + align16(pl.canvas_rows * W);
-  pl.smem_out = pl.smem_buf + align16(pl.canvas_rows * out_w * 4);
-  pl.smem_total = pl.smem_out + align16(out_w * out_h);
+static void drop_render_cache(tbx_pool *p) {
+  cudaFree(p->d_base_gray); cudaFree(p->d_base_rgba);
+  p->d_base_gray = p->d_base_rgba = 0;
+  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out); }
+  p->area.clear();
 }
+/* static frame of the current config, gray and RGBA, on the device */
+static int ensure_base(tbx_pool *p) {
+  if (p->d_base_gray) return TBX_OK;
+  const int npix = p->info->width * p->info->height;
+  p->h_base_rgba.resize(npix);
+  p->h_base_gray.resize(npix);
+  tbx::build_base_frame(p->cfg, p->h_base_rgba.data());
+  tbx::frame_to_gray(p->h_base_rgba.data(), npix, p->h_base_gray.data());
+  CK(cudaMalloc(&p->d_base_gray, npix));
+  CK(cudaMalloc(&p->d_base_rgba, (size_t)npix * 4));
+  CK(cudaMemcpy(p->d_base_gray, p->h_base_gray.data(), npix, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_base_rgba, p->h_base_rgba.data(), (size_t)npix * 4, cudaMemcpyHostToDevice));
+  return TBX_OK;
+}
+static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
+  auto key = std::make_pair(out_w, out_h);
+  auto it = p->area.find(key);
+  if (it == p->area.end()) {
+    tbx::ResizeTab rs;
+    TbxAreaPlan plan;
+    try { tbx::build_resize(p->info->width, p->info->height, out_w, out_h, rs); }
+    catch (const std::exception &e) { return set_err(TBX_EINVAL, e.what()); }
+    if (!tbx::build_area_plan(rs, plan)) return set_err(TBX_EINVAL, "resize: the fused kernel supports destinations up to 128x128 with at most 8 taps per axis");
+    std::vector<uint8_t> base_out(((size_t)out_w * out_h + 15) & ~(size_t)15, 0);
+    tbx::area_resize(p->h_base_gray.data(), rs, base_out.data());
+    AreaRes r;
+    r.dw = out_w; r.dh = out_h; r.d_plan = 0; r.d_base_out = 0;
+    CK(cudaMalloc(&r.d_plan, sizeof plan));
+    CK(cudaMalloc(&r.d_base_out, base_out.size()));
+    CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(r.d_base_out, base_out.data(), base_out.size(), cudaMemcpyHostToDevice));
+    it = p->area.insert(std::make_pair(key, r)).first;
+  }
+  *out = &it->second;
+  return TBX_OK;
+}
+
+static int align16(int v) { return (v + 15) & ~15; }
 
 template <int GAME, int MODE> static int launch_render(const RenderArgs &a, int smem, cudaStream_t s) {
   static int configured = 0; /* per instantiation */
   if (configured < smem) {
-    CK(cudaFuncSetAttribute(render_kernel<GAME, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 200 * 1024 ? smem : 200 * 1024));
-    configured = 200 * 1024 > smem ? 200 * 1024 : smem;
+    const int want = smem > 160 * 1024 ? smem : 160 * 1024;
+    CK(cudaFuncSetAttribute(render_kernel<GAME, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+    configured = want;
   }
   render_kernel<GAME, MODE><<<blocks(a.n, TBX_EPC), TBX_RENDER_THREADS, smem, s>>>(a);
   CK(cudaGetLastError());
@@ -290,21 +310,6 @@ template <int GAME> static int launch_render_mode(int mode, const RenderArgs &a,
   }
 }
 
-static int get_resize(tbx_pool *p, int out_w, int out_h, tbx::ResizeTab **dev, tbx::ResizeTab *host) {
-  try { tbx::build_resize(p->info->width, p->info->height, out_w, out_h, *host); }
-  catch (const std::exception &e) { return set_err(TBX_EINVAL, e.what()); }
-  auto key = std::make_pair(out_w, out_h);
-  auto it = p->d_resize.find(key);
-  if (it == p->d_resize.end()) {
-    tbx::ResizeTab *d = 0;
-    CK(cudaMalloc(&d, sizeof(tbx::ResizeTab)));
-    CK(cudaMemcpy(d, host, sizeof(tbx::ResizeTab), cudaMemcpyHostToDevice));
-    it = p->d_resize.insert(std::make_pair(key, d)).first;
-  }
-  *dev = it->second;
-  return TBX_OK;
-}
-
 extern "C" {
 
 int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream) {
@@ -313,25 +318,39 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   size_t fb = tbx_obs_bytes(p, mode, out_w, out_h);
   if (fb == 0) return set_err(TBX_EINVAL, "unsupported observation layout or size");
   CK(cudaSetDevice(p->device));
+  int r = ensure_base(p);
+  if (r) return r;
+  const int W = p->info->width, H = p->info->height;
+  const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
-  a.dst = dst; a.frame_bytes = fb; a.rs = 0; a.out_w = out_w; a.out_h = out_h;
-  tbx::ResizeTab host_rs;
+  a.dst = dst; a.frame_bytes = fb; a.base = pix == 4 ? p->d_base_rgba : p->d_base_gray; a.base_out = 0; a.plan = 0;
+  a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
+  int smem_total;
   if (mode == TBX_OBS_GRAY_AREA) {
-    tbx::ResizeTab *d = 0;
-    int r = get_resize(p, out_w, out_h, &d, &host_rs);
+    AreaRes *ar = 0;
+    r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
-    a.rs = d;
+    a.base_out = ar->d_base_out; a.plan = ar->d_plan;
+    a.band_rows = H;
+    a.smem_out = a.smem_canvas + align16(W * H + 16);
+    a.smem_plan = a.smem_out + align16(out_w * out_h + 16);
+    a.smem_rects = a.smem_plan + align16((int)sizeof(TbxAreaPlan));
+    smem_total = a.smem_rects + TBX_MAX_RECTS * (int)sizeof(int4);
+  } else {
+    /* canvas bands of at most ~48 KB so several CTAs stay resident per SM */
+    int max_rows = (48 * 1024) / (W * pix);
+    if (max_rows < 1) max_rows = 1;
+    int nb = (H + max_rows - 1) / max_rows;
+    a.band_rows = (H + nb - 1) / nb;
+    a.smem_out = a.smem_plan = a.smem_rects = 0;
+    smem_total = a.smem_canvas + align16(a.band_rows * W * pix);
   }
-  RenderPlan pl;
-  plan_render(p, mode, out_w, out_h, &host_rs, pl);
-  a.band_rows = pl.band_rows; a.canvas_rows = pl.canvas_rows;
-  a.smem_prims = pl.smem_prims; a.smem_canvas = pl.smem_canvas; a.smem_buf = pl.smem_buf; a.smem_out = pl.smem_out;
-  if (pl.smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
+  if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, a, pl.smem_total, s);
-  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, a, pl.smem_total, s);
-  return launch_render_mode<TBX_SPACE_INVADERS>(mode, a, pl.smem_total, s);
+  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, a, smem_total, s);
+  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, a, smem_total, s);
+  return launch_render_mode<TBX_SPACE_INVADERS>(mode, a, smem_total, s);
 }
 
 int tbx_read_scalars(tbx_pool *p, int32_t *score, int32_t *lives, int32_t *level, void *stream) {
@@ -510,6 +529,7 @@ int tbx_config_from_json(tbx_pool *p, const char *json) {
   CK(cudaSetDevice(p->device));
   CK(cudaDeviceSynchronize());
   p->cfg = c;
+  drop_render_cache(p);
   install_default_table(p);
   int r = upload_tables(p);
   if (r) return r;

@@ -187,6 +187,22 @@ typedef struct {
 } TbxResizeAxis;
 typedef struct { TbxResizeAxis x, y; } TbxResizeTab;
 
+/* The same taps repacked for the fused render kernel: every destination index has exactly `tx` / `ty` taps
+ * on consecutive source indices (weights zero-padded; x + 0*b == x exactly for the non-negative sums here),
+ * plus the inverse maps "which destination indices does source index s feed". */
+#define TBX_AREA_MAX_DST 128
+#define TBX_AREA_MAX_TAPS 8
+#define TBX_AREA_MAX_SRC 320
+typedef struct {
+  int32_t sw, sh, dw, dh, tx, ty, _pad[2];
+  uint16_t xs0[TBX_AREA_MAX_DST], ys0[TBX_AREA_MAX_DST];  /* first source index of each destination index */
+  uint16_t yn[TBX_AREA_MAX_DST];                          /* real tap count per destination row */
+  float xalpha[TBX_AREA_MAX_TAPS][TBX_AREA_MAX_DST];      /* [tap][dx]: conflict-free for lanes over dx */
+  float yalpha[TBX_AREA_MAX_TAPS][TBX_AREA_MAX_DST];
+  uint8_t xdlo[TBX_AREA_MAX_SRC], xdhi[TBX_AREA_MAX_SRC]; /* destination columns fed by source column s: [xdlo[s], xdhi[s]] */
+  uint8_t ydlo[TBX_AREA_MAX_SRC], ydhi[TBX_AREA_MAX_SRC];
+} TbxAreaPlan;
+
 #define TBX_WORDS(T) ((int)(sizeof(T) / 4))
 #define TBX_W(T, field) ((int)(offsetof(T, field) / 4))
 

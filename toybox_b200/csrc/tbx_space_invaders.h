@@ -59,6 +59,15 @@
 #define SI_SLOT_SHIP_LASER (SI_SLOT_UFO + 1)
 #define SI_SLOT_ENEMY_LASERS (SI_SLOT_SHIP_LASER + 1)
 #define SI_N_SLOTS (SI_SLOT_ENEMY_LASERS + TBX_SI_MAX_LASERS)
+#define SI_N_STATIC 1
+#define SI_N_GROUPS 4
+/* HUD digits | shields (one colour) | invaders (one colour) | ship, ufo, lasers (in order) */
+TBX_HD void si_group(int g, int &b, int &e, int &mode) {
+  if (g == 0) { b = SI_SLOT_SCORE; e = SI_SLOT_SHIELDS; mode = TBX_GROUP_PARALLEL; }
+  else if (g == 1) { b = SI_SLOT_SHIELDS; e = SI_SLOT_ENEMIES; mode = TBX_GROUP_PARALLEL; }
+  else if (g == 2) { b = SI_SLOT_ENEMIES; e = SI_SLOT_SHIP; mode = TBX_GROUP_PARALLEL; }
+  else { b = SI_SLOT_SHIP; e = SI_N_SLOTS; mode = TBX_GROUP_SERIAL; }
+}
 
 TBX_HD uint32_t si_shield_row_default(int r) { return r < 2 ? 0x0FF0u : r < 10 ? 0x3FFCu : r < 16 ? 0xFFFFu : 0xF00Fu; }
 
