@@ -152,7 +152,7 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
     if (gb != covered) { g_err = "groups do not tile the dynamic slots"; return -1; }
     covered = ge;
     Rect box = {32767, 32767, -1, -1};
-    const bool per_prim = mode == TBX_GROUP_SERIAL && ge - gb <= 32;
+    const bool per_prim = (mode & TBX_GROUP_SERIAL) && ge - gb <= 32;
     for (int s = gb; s < ge; s++) {
       TbxPrim p = get_prim(e, s);
       Rect c = {p.x < 0 ? 0 : p.x, p.y < 0 ? 0 : p.y, p.x + p.w > W ? W : p.x + p.w, p.y + p.h > H ? H : p.y + p.h};

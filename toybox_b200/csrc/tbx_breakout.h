@@ -31,8 +31,9 @@
 #define BRK_N_GROUPS 3
 /* HUD digits (one colour) | bricks (parallel iff the table's rectangles are disjoint) | paddle, balls (in order) */
 TBX_HD void brk_group(int g, const uint32_t *R, const BrkTable *tables, int &b, int &e, int &mode) {
-  if (g == 0) { b = BRK_SLOT_SCORE; e = BRK_SLOT_BRICKS; mode = TBX_GROUP_PARALLEL; }
-  else if (g == 1) { b = BRK_SLOT_BRICKS; e = BRK_SLOT_PADDLE; mode = tables[(int32_t)R[TBX_W(TbxHdr, tbl)]].disjoint ? TBX_GROUP_PARALLEL : TBX_GROUP_SERIAL; }
+  const BrkTable &T = tables[(int32_t)R[TBX_W(TbxHdr, tbl)]];
+  if (g == 0) { b = BRK_SLOT_SCORE; e = BRK_SLOT_BRICKS; mode = TBX_GROUP_PARALLEL | (T.hud_clear ? TBX_GROUP_NOSYNC : 0); }
+  else if (g == 1) { b = BRK_SLOT_BRICKS; e = BRK_SLOT_PADDLE; mode = T.disjoint ? TBX_GROUP_PARALLEL : TBX_GROUP_SERIAL; }
   else { b = BRK_SLOT_PADDLE; e = BRK_N_SLOTS; mode = TBX_GROUP_SERIAL; }
 }
 

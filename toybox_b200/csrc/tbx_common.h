@@ -176,7 +176,7 @@ TBX_HD uint8_t tbx_area_v(const float *buf, int stride, int ys0, const TbxResize
 /* ---- draw-list groups: consecutive slot ranges painted one after the other.  Inside a PARALLEL group no two
  * primitives can conflict (disjoint rectangles, or one colour), so they may be painted in any order; a SERIAL
  * group is painted strictly in slot order. */
-enum { TBX_GROUP_PARALLEL = 0, TBX_GROUP_SERIAL = 1 };
+enum { TBX_GROUP_PARALLEL = 0, TBX_GROUP_SERIAL = 1, TBX_GROUP_NOSYNC = 2 /* flag: provably disjoint from the next group */ };
 
 /* ---- draw-list primitive (16 bytes): a rectangle, optionally masked by a 1-bit sprite.
  * Pixel (px,py) of the rectangle is painted iff bw == 0 or bit (bw-1 - px/sx) of rows[py/sy] is set,

@@ -188,6 +188,8 @@ void brk_finish_table(BrkTable &t) {
   /* NaN coordinates never compare true in the step; make the early-out box permissive in that case */
   if (!(t.bb_x0 == t.bb_x0) || !(t.bb_y0 == t.bb_y0) || !(t.bb_x1 == t.bb_x1) || !(t.bb_y1 == t.bb_y1)) { t.bb_x0 = t.bb_y0 = -INFINITY; t.bb_x1 = t.bb_y1 = INFINITY; }
   for (int i = 0; i < n; i++) if (t.px[i] != t.px[i] || t.py[i] != t.py[i] || t.x1[i] != t.x1[i] || t.y1[i] != t.y1[i]) { t.bb_x0 = t.bb_y0 = -INFINITY; t.bb_x1 = t.bb_y1 = INFINITY; }
+  t.hud_clear = 1;
+  for (int i = 0; i < n; i++) if (t.iw[i] > 0 && t.ih[i] > 0 && t.iy[i] < 12) t.hud_clear = 0;
   t.disjoint = 1;
   for (int i = 0; i < n && t.disjoint; i++)
     for (int j = i + 1; j < n; j++) {

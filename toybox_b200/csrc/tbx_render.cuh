@@ -24,7 +24,12 @@
 
 namespace tbxk {
 
+#ifndef TBX_RENDER_THREADS
 #define TBX_RENDER_THREADS 256
+#endif
+#ifndef TBX_RENDER_MIN_CTAS
+#define TBX_RENDER_MIN_CTAS 4
+#endif
 #define TBX_RENDER_WARPS (TBX_RENDER_THREADS / 32)
 #define TBX_EPC 8
 #define TBX_MAX_GROUPS 4
@@ -129,19 +134,27 @@ __device__ __forceinline__ void paint_coop(typename PixT<PIX>::T *canvas, int r0
   }
 }
 
-/* Paint every dynamic draw-list group of one env into canvas rows [r0,r1), in draw order.  rects (may be NULL):
- * dirty rectangles in native coordinates, rects[g] = bounding box of group g, rects[NG + l] = l-th primitive of
- * the in-order group.  All threads of the CTA must call this. */
+/* warp-wide bounding box of the lanes' clipped rectangles (hardware integer warp reductions) */
+__device__ __forceinline__ int4 warp_bbox(int bx0, int by0, int bx1, int by1) {
+  return make_int4(__reduce_min_sync(0xffffffffu, bx0), __reduce_min_sync(0xffffffffu, by0), __reduce_max_sync(0xffffffffu, bx1),
+                   __reduce_max_sync(0xffffffffu, by1));
+}
+
+/* Paint every dynamic draw-list group of one env into canvas rows [r0,r1), in draw order.  When `rects` is given
+ * the dirty rectangles (native coordinates) are appended to it: one bounding box per group, except that an in-order
+ * group of at most 32 slots contributes one rectangle per primitive (a ball far from the paddle must not dirty
+ * everything in between).  All threads of the CTA must call this; it ends with a barrier. */
 template <int GAME, int PIX>
 __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
-                                          typename PixT<PIX>::T *canvas, int r0, int r1, int4 *rects) {
+                                          typename PixT<PIX>::T *canvas, int r0, int r1, int4 *rects, int *n_rects) {
   typedef Traits<GAME> T;
   constexpr int W = T::W;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int g = 0; g < T::NG; g++) {
     int gb, ge, gmode;
     T::group(g, R, tables, gb, ge, gmode);
-    if (gmode == TBX_GROUP_PARALLEL) {
+    if (gb >= ge) continue; /* empty group (merged into its neighbour): uniform across the CTA, no barrier */
+    if (!(gmode & TBX_GROUP_SERIAL)) {
       int bx0 = 32767, by0 = 32767, bx1 = -1, by1 = -1;
       for (int s0 = gb; s0 < ge; s0 += TBX_RENDER_THREADS) {
         const int s = s0 + tid;
@@ -149,6 +162,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         if (s < ge) p = T::prim(R, cfg, tables, s);
         Clip c;
         const bool ok = clip_prim<W>(p, r0, r1, c);
+        if (!__any_sync(0xffffffffu, ok)) continue;
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
         if (ok) { bx0 = min(bx0, c.x0); by0 = min(by0, c.y0); bx1 = max(bx1, c.x1); by1 = max(by1, c.y1); }
         const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 96;
@@ -170,15 +184,9 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
           }
         }
       }
-      if (rects) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-          bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-        }
-        if (lane == 0 && bx1 > bx0) {
-          atomicMin(&rects[g].x, bx0); atomicMin(&rects[g].y, by0); atomicMax(&rects[g].z, bx1); atomicMax(&rects[g].w, by1);
-        }
+      if (rects && __any_sync(0xffffffffu, bx1 > bx0)) {
+        const int4 bb = warp_bbox(bx0, by0, bx1, by1);
+        if (lane == 0) { atomicMin(&rects[g].x, bb.x); atomicMin(&rects[g].y, bb.y); atomicMax(&rects[g].z, bb.z); atomicMax(&rects[g].w, bb.w); }
       }
     } else if (wid == 0) {
       /* in order: lane l builds primitive gb + 32*batch + l, then the warp paints them one at a time */
@@ -192,8 +200,9 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         const bool ok = clip_prim<W>(p, r0, r1, c);
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
         if (ok) { bx0 = min(bx0, c.x0); by0 = min(by0, c.y0); bx1 = max(bx1, c.x1); by1 = max(by1, c.y1); }
-        if (rects && per_prim_rects && ok) rects[T::NG + lane] = make_int4(c.x0, c.y0, c.x1, c.y1);
         unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (rects && per_prim_rects && ok) rects[T::NG + __popc(m & ((1u << lane) - 1u))] = make_int4(c.x0, c.y0, c.x1, c.y1);
+        if (rects && per_prim_rects && lane == 0) *n_rects = T::NG + __popc(m);
         const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
         const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
         while (m) {
@@ -210,21 +219,18 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         }
       }
       if (rects && !per_prim_rects) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-          bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-        }
-        if (lane == 0 && bx1 > bx0) rects[g] = make_int4(bx0, by0, bx1, by1);
+        const int4 bb = warp_bbox(bx0, by0, bx1, by1);
+        if (lane == 0 && bb.z > bb.x) rects[g] = bb;
       }
     }
-    __syncthreads();
+    if (!(gmode & TBX_GROUP_NOSYNC)) __syncthreads();
   }
 }
 
-/* MODE: TBX_OBS_RGBA (0), TBX_OBS_RGB (1), TBX_OBS_GRAY (2), TBX_OBS_GRAY_AREA (3) */
-template <int GAME, int MODE>
-__global__ void __launch_bounds__(TBX_RENDER_THREADS, 4) render_kernel(RenderArgs a) {
+/* MODE: TBX_OBS_RGBA (0), TBX_OBS_RGB (1), TBX_OBS_GRAY (2), TBX_OBS_GRAY_AREA (3).
+ * TX: taps per output column of the INTER_AREA plan (>= plan.tx; surplus taps carry zero weights). */
+template <int GAME, int MODE, int TX>
+__global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
   constexpr int PIX = (MODE == 0 || MODE == 1) ? 4 : 1;
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, 4) render_kernel(RenderArg
           for (int i = tid; i < n16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
         }
         __syncthreads();
-        paint_env<GAME, PIX>(R, cfg, tables, canvas, r0, r1, (int4 *)0);
+        paint_env<GAME, PIX>(R, cfg, tables, canvas, r0, r1, (int4 *)0, (int *)0);
         if (MODE == 1) {
           /* 16 pixels (64 B of RGBA) -> 48 B of RGB, three 16-byte stores per thread */
           const int groups = (r1 - r0) * W / 16;
@@ -292,66 +298,70 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, 4) render_kernel(RenderArg
     return;
   }
 
-  /* ---- INTER_AREA layout */
-  uint8_t *ostage = smem + a.smem_out;
-  TbxAreaPlan *plan = reinterpret_cast<TbxAreaPlan *>(smem + a.smem_plan);
+  /* ---- INTER_AREA layout.  The staged output is double-buffered so that streaming frame j out overlaps with
+   * staging the base frame for env j+1 (one barrier fewer per env). */
+  const TbxAreaPlan *__restrict__ plan = a.plan; /* read through L1: small, shared by every CTA */
   int4 *rects = reinterpret_cast<int4 *>(smem + a.smem_rects);
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.plan);
-    uint4 *dst = reinterpret_cast<uint4 *>(plan);
-    for (int i = tid; i < (int)(sizeof(TbxAreaPlan) / 16); i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const int dw = plan->dw, dh = plan->dh, tx = plan->tx;
+  int *n_rects = reinterpret_cast<int *>(rects + TBX_MAX_RECTS);
+  const int dw = plan->dw, dh = plan->dh;
   const int nout16 = (dw * dh + 15) / 16;
-  for (int j = 0; j < ne; j++) {
+  const int ostage_bytes = nout16 * 16;
+  for (int j = 0; j <= ne; j++) {
+    if (j > 0) { /* stream frame j-1 out */
+      const uint8_t *ostage = smem + a.smem_out + ((j - 1) & 1) * ostage_bytes;
+      uint8_t *out = a.dst + (size_t)(e0 + j - 1) * a.frame_bytes;
+      if ((a.frame_bytes & 15) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ostage);
+        uint4 *dst = reinterpret_cast<uint4 *>(out);
+        for (int i = tid; i < dw * dh / 16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
+      } else {
+        for (int i = tid; i < dw * dh; i += TBX_RENDER_THREADS) out[i] = ostage[i];
+      }
+    }
+    if (j == ne) break;
     const uint32_t *R = recs + j * RW;
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    uint8_t *ostage = smem + a.smem_out + (j & 1) * ostage_bytes;
     {
       const uint4 *src = reinterpret_cast<const uint4 *>(a.base);
       uint4 *dst = reinterpret_cast<uint4 *>(canvas);
+#pragma unroll 4
       for (int i = tid; i < W * H / 16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
       const uint4 *src2 = reinterpret_cast<const uint4 *>(a.base_out);
       uint4 *dst2 = reinterpret_cast<uint4 *>(ostage);
       for (int i = tid; i < nout16; i += TBX_RENDER_THREADS) dst2[i] = __ldg(src2 + i);
-      if (tid < TBX_MAX_RECTS) rects[tid] = make_int4(32767, 32767, -1, -1);
+      if (tid < T::NG) rects[tid] = make_int4(32767, 32767, -1, -1);
+      if (tid == 0) *n_rects = T::NG;
     }
     __syncthreads();
-    paint_env<GAME, 1>(R, cfg, tables, reinterpret_cast<uint8_t *>(canvas), 0, H, rects);
-    /* recompute the output pixels fed by a dirty rectangle: warp per output row, lanes over columns */
-    for (int r = 0; r < T::NG + 32; r++) {
+    paint_env<GAME, 1>(R, cfg, tables, reinterpret_cast<uint8_t *>(canvas), 0, H, rects, n_rects);
+    /* recompute the output pixels fed by a dirty rectangle: lanes over output columns (per-column taps stay in
+     * registers), warps over output rows */
+    const int nr = *n_rects;
+    for (int r = 0; r < nr; r++) {
       const int4 rc = rects[r];
       if (rc.z <= rc.x) continue;
-      const int dx0 = plan->xdlo[rc.x], dx1 = plan->xdhi[rc.z - 1], dy0 = plan->ydlo[rc.y], dy1 = plan->ydhi[rc.w - 1];
-      for (int dy = dy0 + wid; dy <= dy1; dy += TBX_RENDER_WARPS) {
-        const int ys = plan->ys0[dy], yn = plan->yn[dy];
-        for (int dx = dx0 + lane; dx <= dx1; dx += 32) {
-          const uint8_t *src = reinterpret_cast<const uint8_t *>(canvas) + (size_t)ys * W + plan->xs0[dx];
-          float al[TBX_AREA_MAX_TAPS];
+      const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
+      const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
+      for (int dx = dx0 + lane; dx <= dx1; dx += 32) {
+        const uint8_t *col = reinterpret_cast<const uint8_t *>(canvas) + __ldg(&plan->xs0[dx]);
+        float al[TX];
 #pragma unroll
-          for (int t = 0; t < TBX_AREA_MAX_TAPS; t++) al[t] = t < tx ? plan->xalpha[t][dx] : 0.0f;
+        for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+        for (int dy = dy0 + wid; dy <= dy1; dy += TBX_RENDER_WARPS) {
+          const int yn = __ldg(&plan->yn[dy]);
+          const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
           float v = 0.0f;
-          for (int k = 0; k < yn; k++) {
-            const uint8_t *row = src + (size_t)k * W;
+          for (int k = 0; k < yn; k++, row += W) {
             float h = tbx_fmul((float)row[0], al[0]);
 #pragma unroll
-            for (int t = 1; t < TBX_AREA_MAX_TAPS; t++)
-              if (t < tx) h = tbx_fadd(h, tbx_fmul((float)row[t], al[t]));
-            const float bh = tbx_fmul(plan->yalpha[k][dy], h);
+            for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[t], al[t]));
+            const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
             v = k == 0 ? bh : tbx_fadd(v, bh);
           }
           const int iv = tbx_f2i_rn(v);
           ostage[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
         }
       }
-    }
-    __syncthreads();
-    if ((a.frame_bytes & 15) == 0) {
-      const uint4 *src = reinterpret_cast<const uint4 *>(ostage);
-      uint4 *dst = reinterpret_cast<uint4 *>(out);
-      for (int i = tid; i < dw * dh / 16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
-    } else {
-      for (int i = tid; i < dw * dh; i += TBX_RENDER_THREADS) out[i] = ostage[i];
     }
     __syncthreads();
   }
