@@ -173,3 +173,66 @@ def test_episode_stats(tbx, oracle_mod):
     stats = pool.episode_stats()
     assert stats[0] == episodes
     pool.close()
+
+
+def test_batched_intervention_context_manager(tbx, oracle_mod):
+    from toybox_b200.interventions import BatchedIntervention, parse_property_access
+    assert parse_property_access("abc.def[7][8].y[5]") == ["abc", "def", 7, 8, "y", 5]      # test_get_property.py:76-78
+    n = 16
+    pool = tbx.BatchedToybox("space_invaders", n, seeds=5)
+    ref = oracle_mod.OracleBatch("space_invaders", n, seeds=5 + np.arange(n))
+    ids = [1, 4, 9]
+    with BatchedIntervention(pool, ids) as iv:
+        iv.set("lives", 1)
+        iv.set("ufo.appearance_counter", [3, 4, 5])
+        assert iv.get("ship.x") == [68, 68, 68]
+    assert iv.dirty_state and not iv.dirty_config
+    for k, i in enumerate(ids):
+        js = ref.state_json(i)
+        js["lives"] = 1
+        js["ufo"]["appearance_counter"] = 3 + k
+        ref.write_state_json(i, js)
+    for t in range(300):
+        acts = actions_for(oracle_mod, "space_invaders", n, t)
+        pool.apply_ale_action(acts, auto_reset=True)
+        r, d, s, l = ref.step(acts, auto_reset=True)
+        assert np.array_equal(pool.lives.cpu().numpy(), l), t
+    for i in range(n):
+        assert json_diff(pool.to_state_json([i])[0], ref.state_json(i)) == [], i
+    with BatchedIntervention(pool) as iv:
+        iv.config["start_lives"] = 7
+    assert iv.dirty_config
+    assert int(pool.get_lives().min()) == 7
+    pool.close()
+
+
+def test_ctoybox_shim_and_env_surface(tbx, oracle_mod):
+    """The batch-1 drop-in (`toybox_b200.ctoybox.Toybox`) and the gym-free env classes behave like the reference's."""
+    from toybox_b200.ctoybox import Toybox, Input
+    from toybox_b200.envs import BreakoutEnv, BatchedToyboxEnv
+    with Toybox("breakout") as tb:
+        ref = oracle_mod.OracleToybox("breakout")
+        fire = Input()
+        fire.button1 = True
+        tb.apply_action(fire)
+        ref.apply_action(fire)
+        for a in [3, 3, 4, 0, 1] * 30:
+            tb.apply_ale_action(a)
+            ref.apply_ale_action(a)
+        assert json_diff(tb.to_state_json(), ref.to_state_json()) == []
+        assert tb.get_state().shape == (160, 240, 1) and np.array_equal(tb.get_state(), ref.get_state())
+        assert np.array_equal(tb.get_rgb_frame(), ref.get_rgb_frame())
+        assert tb.get_legal_action_set() == [0, 1, 3, 4] and tb.get_lives() == ref.get_lives() and not tb.game_over()
+        with pytest.raises(ValueError):
+            tb.apply_ale_action(42)
+        assert tb.query_state_json("bricks_remaining") == 108
+    env = BreakoutEnv(grayscale=False)
+    obs = env.reset()
+    assert obs.shape == (160, 240, 3)
+    obs, reward, done, info = env.step(1)
+    assert reward == 0 and not done and info["lives"] == 5 and env.ale.getScreenRGB().shape == (160, 240, 3)
+    env.close()
+    benv = BatchedToyboxEnv("amidar", 32, seed=3)
+    obs, reward, done, info = benv.step(np.zeros(32, np.int64))
+    assert tuple(obs.shape) == (32, 84, 84, 1) and int(info["lives"].min()) == 3
+    benv.close()
