@@ -17,7 +17,7 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out; int dw, dh, tx; };
+struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out; int dw, dh, tx, ty; };
 static void drop_render_cache(struct tbx_pool *p);
 
 struct tbx_pool {
@@ -277,7 +277,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     std::vector<uint8_t> base_out(((size_t)out_w * out_h + 15) & ~(size_t)15, 0);
     tbx::area_resize(p->h_base_gray.data(), rs, base_out.data());
     AreaRes r;
-    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.d_plan = 0; r.d_base_out = 0;
+    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
     CK(cudaMalloc(&r.d_base_out, base_out.size()));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
@@ -290,27 +290,32 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
 
 static int align16(int v) { return (v + 15) & ~15; }
 
-template <int GAME, int MODE, int TX> static int launch_render(const RenderArgs &a, int smem, cudaStream_t s) {
+template <int GAME, int MODE, int TX, int TY> static int launch_render(const RenderArgs &a, int smem, cudaStream_t s) {
   static int configured = 0; /* per instantiation */
   if (configured < smem) {
     const int want = smem > 160 * 1024 ? smem : 160 * 1024;
-    CK(cudaFuncSetAttribute(render_kernel<GAME, MODE, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+    CK((cudaFuncSetAttribute(render_kernel<GAME, MODE, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)));
     configured = want;
   }
-  render_kernel<GAME, MODE, TX><<<blocks(a.n, TBX_EPC), TBX_RENDER_THREADS, smem, s>>>(a);
+  render_kernel<GAME, MODE, TX, TY><<<blocks(a.n, TBX_EPC), TBX_RENDER_THREADS, smem, s>>>(a);
   CK(cudaGetLastError());
   return TBX_OK;
 }
-template <int GAME> static int launch_render_mode(int mode, int tx, const RenderArgs &a, int smem, cudaStream_t s) {
+/* INTER_AREA: the smallest instantiated tap counts that cover the plan */
+template <int GAME, int TY> static int launch_area_tx(int tx, const RenderArgs &a, int smem, cudaStream_t s) {
+  if (tx <= 3) return launch_render<GAME, TBX_OBS_GRAY_AREA, 3, TY>(a, smem, s);
+  if (tx <= 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 4, TY>(a, smem, s);
+  return launch_render<GAME, TBX_OBS_GRAY_AREA, 5, TY>(a, smem, s);
+}
+template <int GAME> static int launch_render_mode(int mode, int tx, int ty, const RenderArgs &a, int smem, cudaStream_t s) {
   switch (mode) {
-    case TBX_OBS_RGBA: return launch_render<GAME, TBX_OBS_RGBA, 1>(a, smem, s);
-    case TBX_OBS_RGB: return launch_render<GAME, TBX_OBS_RGB, 1>(a, smem, s);
-    case TBX_OBS_GRAY: return launch_render<GAME, TBX_OBS_GRAY, 1>(a, smem, s);
-    default: /* INTER_AREA: smallest instantiated tap count that covers the plan (surplus taps have zero weight) */
-      if (tx <= 3) return launch_render<GAME, TBX_OBS_GRAY_AREA, 3>(a, smem, s);
-      if (tx <= 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 4>(a, smem, s);
-      if (tx <= 5) return launch_render<GAME, TBX_OBS_GRAY_AREA, 5>(a, smem, s);
-      return launch_render<GAME, TBX_OBS_GRAY_AREA, 8>(a, smem, s);
+    case TBX_OBS_RGBA: return launch_render<GAME, TBX_OBS_RGBA, 1, 1>(a, smem, s);
+    case TBX_OBS_RGB: return launch_render<GAME, TBX_OBS_RGB, 1, 1>(a, smem, s);
+    case TBX_OBS_GRAY: return launch_render<GAME, TBX_OBS_GRAY, 1, 1>(a, smem, s);
+    default:
+      if (tx > 5 || ty > 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 8, 8>(a, smem, s);
+      if (ty <= 3) return launch_area_tx<GAME, 3>(tx, a, smem, s);
+      return launch_area_tx<GAME, 4>(tx, a, smem, s);
   }
 }
 
@@ -330,15 +335,17 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.dst = dst; a.frame_bytes = fb; a.base = pix == 4 ? p->d_base_rgba : p->d_base_gray; a.base_out = 0; a.plan = 0;
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
-  int smem_total, tx = 1;
+  int smem_total, tx = 1, ty = 1;
   if (mode == TBX_OBS_GRAY_AREA) {
     AreaRes *ar = 0;
     r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
     a.base_out = ar->d_base_out; a.plan = ar->d_plan;
     a.band_rows = H;
-    tx = ar->tx;
-    a.smem_out = a.smem_canvas + align16(W * H + 16);
+    tx = ar->tx; ty = ar->ty;
+    /* surplus (zero-weight) taps may read up to TY-1 rows past the canvas: keep them inside the allocation */
+    const int ty_inst = (tx > 5 || ty > 4) ? 8 : (ty <= 3 ? 3 : 4);
+    a.smem_out = a.smem_canvas + align16(W * H + (ty_inst - 1) * W + 16);
     a.smem_rects = a.smem_out + 2 * align16(out_w * out_h);
     a.smem_plan = 0;
     smem_total = a.smem_rects + TBX_MAX_RECTS * (int)sizeof(int4) + 16;
@@ -353,9 +360,9 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   }
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, a, smem_total, s);
-  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, a, smem_total, s);
-  return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, a, smem_total, s);
+  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, smem_total, s);
+  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, ty, a, smem_total, s);
+  return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, ty, a, smem_total, s);
 }
 
 int tbx_read_scalars(tbx_pool *p, int32_t *score, int32_t *lives, int32_t *level, void *stream) {

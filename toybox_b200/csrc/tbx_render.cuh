@@ -228,8 +228,8 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
 }
 
 /* MODE: TBX_OBS_RGBA (0), TBX_OBS_RGB (1), TBX_OBS_GRAY (2), TBX_OBS_GRAY_AREA (3).
- * TX: taps per output column of the INTER_AREA plan (>= plan.tx; surplus taps carry zero weights). */
-template <int GAME, int MODE, int TX>
+ * TX, TY: taps per output column / row of the INTER_AREA plan (>= plan.tx, plan.ty; surplus taps have zero weight). */
+template <int GAME, int MODE, int TX, int TY>
 __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
@@ -334,32 +334,38 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
     }
     __syncthreads();
     paint_env<GAME, 1>(R, cfg, tables, reinterpret_cast<uint8_t *>(canvas), 0, H, rects, n_rects);
-    /* recompute the output pixels fed by a dirty rectangle: lanes over output columns (per-column taps stay in
-     * registers), warps over output rows */
+    /* recompute the output pixels fed by a dirty rectangle.  Lanes own output columns (their taps stay in
+     * registers), warps own output rows; narrow rectangles pack several rows into one warp.  The tap loops are
+     * straight-line: TX x TY taps, surplus taps carry zero weights (x + 0*b == x exactly for these sums). */
     const int nr = *n_rects;
     for (int r = 0; r < nr; r++) {
       const int4 rc = rects[r];
       if (rc.z <= rc.x) continue;
       const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
       const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
-      for (int dx = dx0 + lane; dx <= dx1; dx += 32) {
+      const int ncols = dx1 - dx0 + 1;
+      const int lg = ncols > 16 ? 5 : ncols > 8 ? 4 : ncols > 4 ? 3 : 2; /* columns per warp pass = 1 << lg */
+      const int cpl = 1 << lg, rpi = 32 >> lg, sub = lane >> lg, c = lane & (cpl - 1);
+      for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
+        const bool colok = dxb + c <= dx1;
+        const int dx = colok ? dxb + c : dx1;
         const uint8_t *col = reinterpret_cast<const uint8_t *>(canvas) + __ldg(&plan->xs0[dx]);
         float al[TX];
 #pragma unroll
         for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
-        for (int dy = dy0 + wid; dy <= dy1; dy += TBX_RENDER_WARPS) {
-          const int yn = __ldg(&plan->yn[dy]);
+        for (int dy = dy0 + wid * rpi + sub; dy <= dy1; dy += TBX_RENDER_WARPS * rpi) {
           const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
           float v = 0.0f;
-          for (int k = 0; k < yn; k++, row += W) {
-            float h = tbx_fmul((float)row[0], al[0]);
 #pragma unroll
-            for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[t], al[t]));
+          for (int k = 0; k < TY; k++) {
+            float h = tbx_fmul((float)row[k * W], al[0]);
+#pragma unroll
+            for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[k * W + t], al[t]));
             const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
             v = k == 0 ? bh : tbx_fadd(v, bh);
           }
           const int iv = tbx_f2i_rn(v);
-          ostage[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+          if (colok) ostage[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
         }
       }
     }
