@@ -36,7 +36,7 @@ template <class TT> static int intern(std::vector<TT> &v, const TT &t) {
   return (int)v.size() - 1;
 }
 static void install_default_table(Emu *e) {
-  if (e->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(e->cfg.brk, t); e->cfg.brk.default_tbl = intern(e->brk_tables, t); }
+  if (e->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(e->cfg.brk, t); tbx::brk_mark_delta_ok(e->cfg, t); e->cfg.brk.default_tbl = intern(e->brk_tables, t); }
   else if (e->game == TBX_AMIDAR) { AmiTable t; tbx::ami_default_table(e->cfg.ami, t); e->cfg.ami.default_tbl = intern(e->ami_tables, t); }
 }
 static void new_game(Emu *e) {
@@ -135,9 +135,11 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
   TbxAreaPlan pl;
   try { tbx::build_resize(W, H, out_w, out_h, rs); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
   if (!tbx::build_area_plan(rs, pl)) { g_err = "size pair outside the fused kernel's limits"; return -1; }
+  const int base_id = e->game == TBX_BREAKOUT ? brk_base_id(e->rec.data(), e->cfg.brk, e->brk_tables.data())
+                      : e->game == TBX_AMIDAR ? ami_base_id(e->rec.data(), e->cfg.ami, e->ami_tables.data()) : 0;
   std::vector<uint32_t> base((size_t)W * H);
-  tbx::build_base_frame(e->cfg, base.data());
-  std::vector<uint8_t> canvas((size_t)W * H + 16, 0);
+  tbx::build_base_frame(e->cfg, e->game == TBX_BREAKOUT ? &e->brk_tables[e->cfg.brk.default_tbl] : 0, base_id, base.data());
+  std::vector<uint8_t> canvas((size_t)W * H + 8 * W + 16, 0);
   tbx::frame_to_gray(base.data(), W * H, canvas.data());
   tbx::area_resize(canvas.data(), rs, out);
   struct Rect { int x0, y0, x1, y1; };
@@ -154,7 +156,8 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
     Rect box = {32767, 32767, -1, -1};
     const bool per_prim = (mode & TBX_GROUP_SERIAL) && ge - gb <= 32;
     for (int s = gb; s < ge; s++) {
-      TbxPrim p = get_prim(e, s);
+      TbxPrim p = e->game == TBX_BREAKOUT ? brk_prim_delta(e->rec.data(), e->cfg.brk, e->brk_tables.data(), s, base_id)
+                  : e->game == TBX_AMIDAR ? ami_prim_delta(e->rec.data(), e->cfg.ami, e->ami_tables.data(), s, base_id) : si_prim(e->rec.data(), s);
       Rect c = {p.x < 0 ? 0 : p.x, p.y < 0 ? 0 : p.y, p.x + p.w > W ? W : p.x + p.w, p.y + p.h > H ? H : p.y + p.h};
       if (p.h <= 0 || c.x0 >= c.x1 || c.y0 >= c.y1) continue;
       uint8_t val = (uint8_t)tbx_luma(p.color);
@@ -174,10 +177,10 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
       for (int dx = dx0; dx <= dx1; dx++) {
         const uint8_t *src = canvas.data() + (size_t)pl.ys0[dy] * W + pl.xs0[dx];
         float v = 0.0f;
-        for (int k = 0; k < pl.yn[dy]; k++) {
+        for (int k = 0; k < TBX_AREA_MAX_TAPS; k++) { /* zero-padded taps, as the kernel's fixed TY */
           const uint8_t *row = src + (size_t)k * W;
           float h = tbx_fmul((float)row[0], pl.xalpha[0][dx]);
-          for (int t = 1; t < pl.tx; t++) h = tbx_fadd(h, tbx_fmul((float)row[t], pl.xalpha[t][dx]));
+          for (int t = 1; t < TBX_AREA_MAX_TAPS; t++) h = tbx_fadd(h, tbx_fmul((float)row[t], pl.xalpha[t][dx])); /* zero-padded taps */
           const float bh = tbx_fmul(pl.yalpha[k][dy], h);
           v = k == 0 ? bh : tbx_fadd(v, bh);
         }
@@ -201,7 +204,7 @@ int emu_state_from_json(Emu *e, const char *json) {
   std::vector<uint32_t> rec = e->rec;
   try {
     Value v = tbxjson::parse(json);
-    if (e->game == TBX_BREAKOUT) { BrkTable t; BrkRec &r = *reinterpret_cast<BrkRec *>(rec.data()); tbx::brk_state_from_json(v, r, t); r.hdr.tbl = intern(e->brk_tables, t); }
+    if (e->game == TBX_BREAKOUT) { BrkTable t; BrkRec &r = *reinterpret_cast<BrkRec *>(rec.data()); tbx::brk_state_from_json(v, r, t); tbx::brk_mark_delta_ok(e->cfg, t); r.hdr.tbl = intern(e->brk_tables, t); }
     else if (e->game == TBX_AMIDAR) { AmiTable t; AmiRec &r = *reinterpret_cast<AmiRec *>(rec.data()); tbx::ami_state_from_json(v, r, t); r.hdr.tbl = intern(e->ami_tables, t); }
     else tbx::si_state_from_json(v, *reinterpret_cast<SiRec *>(rec.data()));
   } catch (const std::exception &ex) { g_err = ex.what(); return -1; }

@@ -62,3 +62,39 @@ def test_fused_with_interventions_and_sizes(oracle_mod):
     assert np.array_equal(a.render_fast(), a.render("gray84"))
     with pytest.raises(ValueError):
         a.render_fast(16, 16)       # more than 8 taps per axis: outside the fused kernel's limits
+
+
+def test_delta_bases(oracle_mod):
+    """Base frame 1 (fresh-game look) + deltas: dead bricks on the default table, painted / emptied Amidar tiles;
+    an env whose brick table differs falls back to base 0 with every alive brick painted."""
+    rng = np.random.default_rng(3)
+    b = emu_lib.Emu("breakout")
+    js = b.state_json()
+    for i in rng.choice(108, size=40, replace=False):
+        js["bricks"][int(i)]["alive"] = False
+    b.write_state_json(js)
+    assert b.n_tables() == 1                                 # still the default table -> base 1
+    assert np.array_equal(b.render_fast(), b.render("gray84"))
+    for br in js["bricks"]:
+        br["alive"] = False
+    js["bricks"][7]["alive"] = True
+    b.write_state_json(js)
+    assert np.array_equal(b.render_fast(), b.render("gray84"))
+    js["bricks"][50]["points"] = 3                           # a different table -> base 0
+    b.write_state_json(js)
+    assert b.n_tables() == 2
+    assert np.array_equal(b.render_fast(), b.render("gray84"))
+    cfg = b.config_json()
+    cfg["frame_color"] = cfg["bg_color"]                     # bricks would sit on non-distinguishable walls: still exact
+    cfg["row_colors"][0] = {"r": 1, "g": 1, "b": 1, "a": 255}
+    b.write_config_json(cfg)
+    b.new_game()
+    assert np.array_equal(b.render_fast(), b.render("gray84"))
+    a = emu_lib.Emu("amidar")
+    js = a.state_json()
+    for ty in range(31):
+        for tx in range(32):
+            if rng.random() < 0.3:
+                js["board"]["tiles"][ty][tx] = ["Empty", "Unpainted", "ChaseMarker", "Painted"][int(rng.integers(4))]
+    a.write_state_json(js)
+    assert np.array_equal(a.render_fast(), a.render("gray84"))

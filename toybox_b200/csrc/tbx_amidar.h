@@ -474,4 +474,20 @@ TBX_HD TbxPrim ami_prim(const uint32_t *R, const AmiCfg &c, const AmiTable *tabl
   return tbx_prim_digit(c.painted_color, 144, 205, S.ldi(AMI_W(jumps)), 2, 2, slot - AMI_SLOT_JUMPS);
 }
 
+/* Delta rendering.  Base frame 1 holds the config's board (every tile as new_game lays it out); the tile grid is
+ * fixed and sits on the background, so an env is base 1 plus the tiles whose LOOK (empty / unpainted / painted)
+ * differs from the config board, painted in their current look. */
+TBX_HD int ami_tile_look(int t) { return t == TBX_TILE_EMPTY ? 0 : t == TBX_TILE_PAINTED ? 2 : 1; }
+TBX_HD int ami_base_id(const uint32_t *, const AmiCfg &, const AmiTable *) { return 1; }
+TBX_HD TbxPrim ami_prim_delta(const uint32_t *R, const AmiCfg &c, const AmiTable *tables, int slot, int base) {
+  if (base == 1 && slot < AMI_SLOT_BOXES) {
+    int tx = slot & 31, ty = slot >> 5;
+    int look = ami_tile_look((int)((R[AMI_W(tiles) + 2 * ty + (tx >> 4)] >> (2 * (tx & 15))) & 3u));
+    int ref = ami_tile_look((int)((c.board[ty][tx >> 4] >> (2 * (tx & 15))) & 3u));
+    if (look == ref) return tbx_prim_none();
+    return tbx_prim_rect(look == 0 ? c.bg_color : look == 2 ? c.painted_color : c.unpainted_color, AMI_OFF_X + 4 * tx, AMI_OFF_Y + 5 * ty, 4, 5);
+  }
+  return ami_prim(R, c, tables, slot);
+}
+
 #endif

@@ -255,4 +255,22 @@ TBX_HD TbxPrim brk_prim(const uint32_t *R, const BrkCfg &c, const BrkTable *tabl
   return tbx_prim_rect(c.ball_color, tbx_d2i(tbx_dsub(S.ldd(w), r)), tbx_d2i(tbx_dsub(S.ldd(w + 2), r)), tbx_d2i(d), tbx_d2i(d));
 }
 
+/* Delta rendering.  Base frame 0 holds the static slots only; base frame 1 additionally holds every brick of the
+ * config's default table alive.  An env on that table (when the table is `delta_ok`: disjoint bricks lying on
+ * pure background, clear of the HUD) is drawn as base 1 plus its DEAD bricks painted in the background colour --
+ * the same pixels the painter's algorithm yields, with work proportional to what differs from a fresh game. */
+TBX_HD int brk_base_id(const uint32_t *R, const BrkCfg &c, const BrkTable *tables) {
+  int t = (int32_t)R[TBX_HW(tbl)];
+  return (t == c.default_tbl && tables[t].delta_ok) ? 1 : 0;
+}
+TBX_HD TbxPrim brk_prim_delta(const uint32_t *R, const BrkCfg &c, const BrkTable *tables, int slot, int base) {
+  if (base == 1 && slot >= BRK_SLOT_BRICKS && slot < BRK_SLOT_PADDLE) {
+    int i = slot - BRK_SLOT_BRICKS;
+    const BrkTable &T = tables[(int32_t)R[TBX_HW(tbl)]];
+    if (i >= T.n_bricks || ((R[BRK_W(alive) + (i >> 5)] >> (i & 31)) & 1u)) return tbx_prim_none();
+    return tbx_prim_rect(c.bg_color, T.ix[i], T.iy[i], T.iw[i], T.ih[i]);
+  }
+  return brk_prim(R, c, tables, slot);
+}
+
 #endif

@@ -833,7 +833,13 @@ bool build_area_plan(const ResizeTab &t, TbxAreaPlan &pl) {
 
 int n_static_slots(int game) { return game == TBX_BREAKOUT ? BRK_N_STATIC : game == TBX_AMIDAR ? AMI_N_STATIC : SI_N_STATIC; }
 static const uint32_t HOST_BANK[TBX_BANK_WORDS] = TBX_BANK_INIT;
-void build_base_frame(const Config &c, uint32_t *rgba) {
+static void paint_prim_host(const TbxPrim &p, const uint32_t *rec, int W, int H, uint32_t *rgba) {
+  if (p.h <= 0) return;
+  for (int y = p.y < 0 ? 0 : p.y; y < p.y + p.h && y < H; y++)
+    for (int x = p.x < 0 ? 0 : p.x; x < p.x + p.w && x < W; x++)
+      if (tbx_prim_covers(p, HOST_BANK, rec, x, y)) rgba[(size_t)y * W + x] = p.color;
+}
+void build_base_frame(const Config &c, const BrkTable *brk_default, int base_id, uint32_t *rgba) {
   const GameInfo *gi = game_info(c.game);
   const int W = gi->width, H = gi->height;
   uint32_t clearv = c.game == TBX_BREAKOUT ? c.brk.bg_color : c.game == TBX_AMIDAR ? c.ami.bg_color : SI_COLOR_BLACK;
@@ -841,11 +847,30 @@ void build_base_frame(const Config &c, uint32_t *rgba) {
   std::vector<uint32_t> rec(gi->rec_words, 0); /* static slots never read the record */
   for (int s = 0; s < n_static_slots(c.game); s++) {
     TbxPrim p = c.game == TBX_BREAKOUT ? brk_prim(rec.data(), c.brk, 0, s) : c.game == TBX_AMIDAR ? ami_prim(rec.data(), c.ami, 0, s) : si_prim(rec.data(), s);
-    if (p.h <= 0) continue;
-    for (int y = p.y < 0 ? 0 : p.y; y < p.y + p.h && y < H; y++)
-      for (int x = p.x < 0 ? 0 : p.x; x < p.x + p.w && x < W; x++)
-        if (tbx_prim_covers(p, HOST_BANK, rec.data(), x, y)) rgba[(size_t)y * W + x] = p.color;
+    paint_prim_host(p, rec.data(), W, H, rgba);
   }
+  if (base_id != 1) return;
+  if (c.game == TBX_BREAKOUT && brk_default) {
+    BrkRec &r = *reinterpret_cast<BrkRec *>(rec.data());
+    r.hdr.tbl = 0; /* brk_default is passed as table 0 */
+    for (int k = 0; k < 5; k++) r.alive[k] = brk_default->all_mask[k];
+    for (int s = BRK_SLOT_BRICKS; s < BRK_SLOT_PADDLE; s++) paint_prim_host(brk_prim(rec.data(), c.brk, brk_default, s), rec.data(), W, H, rgba);
+  } else if (c.game == TBX_AMIDAR) {
+    AmiRec &r = *reinterpret_cast<AmiRec *>(rec.data());
+    for (int ty = 0; ty < TBX_AMI_BH; ty++) { r.tiles[ty][0] = c.ami.board[ty][0]; r.tiles[ty][1] = c.ami.board[ty][1]; }
+    for (int s = AMI_SLOT_TILES; s < AMI_SLOT_BOXES; s++) paint_prim_host(ami_prim(rec.data(), c.ami, 0, s), rec.data(), W, H, rgba);
+  }
+}
+void brk_mark_delta_ok(const Config &c, BrkTable &t) {
+  t.delta_ok = 0;
+  if (c.game != TBX_BREAKOUT || !t.disjoint || !t.hud_clear) return;
+  std::vector<uint32_t> base0((size_t)TBX_BRK_W * TBX_BRK_H);
+  build_base_frame(c, 0, 0, base0.data());
+  for (int i = 0; i < t.n_bricks; i++)
+    for (int y = t.iy[i] < 0 ? 0 : t.iy[i]; y < t.iy[i] + t.ih[i] && y < TBX_BRK_H; y++)
+      for (int x = t.ix[i] < 0 ? 0 : t.ix[i]; x < t.ix[i] + t.iw[i] && x < TBX_BRK_W; x++)
+        if (base0[(size_t)y * TBX_BRK_W + x] != c.brk.bg_color) return;
+  t.delta_ok = 1;
 }
 void frame_to_gray(const uint32_t *rgba, int npix, uint8_t *gray) { for (int i = 0; i < npix; i++) gray[i] = (uint8_t)tbx_luma(rgba[i]); }
 void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out) {

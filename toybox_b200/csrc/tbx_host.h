@@ -70,7 +70,11 @@ bool build_area_plan(const ResizeTab &t, TbxAreaPlan &plan);
 /* Static part of a game's frame: the leading draw-list slots that depend on the config only (Breakout: frame
  * walls; Space Invaders: ground line; Amidar: none) painted over the clear colour.  rgba: W*H pixels. */
 int n_static_slots(int game);
-void build_base_frame(const Config &c, uint32_t *rgba);
+/* base_id 0: static slots only.  base_id 1: plus the reference (new_game) look of the delta-rendered group --
+ * Breakout: every brick of `brk_default` alive; Amidar: the config board's tiles (tbx_*_prim_delta). */
+void build_base_frame(const Config &c, const BrkTable *brk_default, int base_id, uint32_t *rgba);
+/* sets t.delta_ok for the config (same answer for identical tables, so interning is unaffected) */
+void brk_mark_delta_ok(const Config &c, BrkTable &t);
 /* gray bytes of an RGBA frame, and its INTER_AREA down-sample (same arithmetic as the kernels) */
 void frame_to_gray(const uint32_t *rgba, int npix, uint8_t *gray);
 void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out);

@@ -17,7 +17,7 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out; int dw, dh, tx, ty; };
+struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out[2]; int dw, dh, tx, ty; };
 static void drop_render_cache(struct tbx_pool *p);
 
 struct tbx_pool {
@@ -34,9 +34,9 @@ struct tbx_pool {
   int *d_bad;
   int32_t *d_legal;
   /* render resources of the current config: static frame (gray, RGBA) and per output size the INTER_AREA plan */
-  uint8_t *d_base_gray, *d_base_rgba;
-  std::vector<uint32_t> h_base_rgba;
-  std::vector<uint8_t> h_base_gray;
+  uint8_t *d_base_gray[2], *d_base_rgba[2];
+  std::vector<uint32_t> h_base_rgba[2];
+  std::vector<uint8_t> h_base_gray[2];
   std::map<std::pair<int, int>, struct AreaRes> area;
   /* tbx_step_host staging */
   cudaStream_t hs;
@@ -79,7 +79,7 @@ template <class TT> static int intern(std::vector<TT> &v, const TT &t) {
   return (int)v.size() - 1;
 }
 static void install_default_table(tbx_pool *p) {
-  if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(p->cfg.brk, t); p->cfg.brk.default_tbl = intern(p->brk_tables, t); }
+  if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_default_table(p->cfg.brk, t); tbx::brk_mark_delta_ok(p->cfg, t); p->cfg.brk.default_tbl = intern(p->brk_tables, t); }
   else if (p->game == TBX_AMIDAR) { AmiTable t; tbx::ami_default_table(p->cfg.ami, t); p->cfg.ami.default_tbl = intern(p->ami_tables, t); }
 }
 
@@ -124,7 +124,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   tbx_pool *p = new (std::nothrow) tbx_pool();
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
-  p->d_cfg = p->d_tables = 0; p->d_base_gray = p->d_base_rgba = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
+  p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
   p->hs = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
@@ -246,23 +246,25 @@ int tbx_check(tbx_pool *p, void *stream) {
 
 /* ---- render */
 static void drop_render_cache(tbx_pool *p) {
-  cudaFree(p->d_base_gray); cudaFree(p->d_base_rgba);
-  p->d_base_gray = p->d_base_rgba = 0;
-  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out); }
+  for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); p->d_base_gray[b] = p->d_base_rgba[b] = 0; }
+  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); }
   p->area.clear();
 }
-/* static frame of the current config, gray and RGBA, on the device */
+/* base frames 0/1 of the current config (see tbx_render.cuh), gray and RGBA, on the device */
 static int ensure_base(tbx_pool *p) {
-  if (p->d_base_gray) return TBX_OK;
+  if (p->d_base_gray[0]) return TBX_OK;
   const int npix = p->info->width * p->info->height;
-  p->h_base_rgba.resize(npix);
-  p->h_base_gray.resize(npix);
-  tbx::build_base_frame(p->cfg, p->h_base_rgba.data());
-  tbx::frame_to_gray(p->h_base_rgba.data(), npix, p->h_base_gray.data());
-  CK(cudaMalloc(&p->d_base_gray, npix));
-  CK(cudaMalloc(&p->d_base_rgba, (size_t)npix * 4));
-  CK(cudaMemcpy(p->d_base_gray, p->h_base_gray.data(), npix, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(p->d_base_rgba, p->h_base_rgba.data(), (size_t)npix * 4, cudaMemcpyHostToDevice));
+  const BrkTable *brk_default = p->game == TBX_BREAKOUT ? &p->brk_tables[p->cfg.brk.default_tbl] : 0;
+  for (int b = 0; b < 2; b++) {
+    p->h_base_rgba[b].resize(npix);
+    p->h_base_gray[b].resize(npix);
+    tbx::build_base_frame(p->cfg, brk_default, b, p->h_base_rgba[b].data());
+    tbx::frame_to_gray(p->h_base_rgba[b].data(), npix, p->h_base_gray[b].data());
+    CK(cudaMalloc(&p->d_base_gray[b], npix));
+    CK(cudaMalloc(&p->d_base_rgba[b], (size_t)npix * 4));
+    CK(cudaMemcpy(p->d_base_gray[b], p->h_base_gray[b].data(), npix, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_base_rgba[b], p->h_base_rgba[b].data(), (size_t)npix * 4, cudaMemcpyHostToDevice));
+  }
   return TBX_OK;
 }
 static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
@@ -274,14 +276,16 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     try { tbx::build_resize(p->info->width, p->info->height, out_w, out_h, rs); }
     catch (const std::exception &e) { return set_err(TBX_EINVAL, e.what()); }
     if (!tbx::build_area_plan(rs, plan)) return set_err(TBX_EINVAL, "resize: the fused kernel supports destinations up to 128x128 with at most 8 taps per axis");
-    std::vector<uint8_t> base_out(((size_t)out_w * out_h + 15) & ~(size_t)15, 0);
-    tbx::area_resize(p->h_base_gray.data(), rs, base_out.data());
     AreaRes r;
-    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out = 0;
+    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
-    CK(cudaMalloc(&r.d_base_out, base_out.size()));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(r.d_base_out, base_out.data(), base_out.size(), cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2; b++) {
+      std::vector<uint8_t> base_out(((size_t)out_w * out_h + 15) & ~(size_t)15, 0);
+      tbx::area_resize(p->h_base_gray[b].data(), rs, base_out.data());
+      CK(cudaMalloc(&r.d_base_out[b], base_out.size()));
+      CK(cudaMemcpy(r.d_base_out[b], base_out.data(), base_out.size(), cudaMemcpyHostToDevice));
+    }
     it = p->area.insert(std::make_pair(key, r)).first;
   }
   *out = &it->second;
@@ -297,7 +301,9 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
     CK((cudaFuncSetAttribute(render_kernel<GAME, MODE, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)));
     configured = want;
   }
-  render_kernel<GAME, MODE, TX, TY><<<blocks(a.n, TBX_EPC), TBX_RENDER_THREADS, smem, s>>>(a);
+  const int H = Traits<GAME>::H;
+  dim3 grid(blocks(a.n, TBX_EPC), MODE == TBX_OBS_GRAY_AREA ? 1 : (H + a.band_rows - 1) / a.band_rows);
+  render_kernel<GAME, MODE, TX, TY><<<grid, TBX_RENDER_THREADS, smem, s>>>(a);
   CK(cudaGetLastError());
   return TBX_OK;
 }
@@ -333,31 +339,29 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
-  a.dst = dst; a.frame_bytes = fb; a.base = pix == 4 ? p->d_base_rgba : p->d_base_gray; a.base_out = 0; a.plan = 0;
+  a.dst = dst; a.frame_bytes = fb; a.plan = 0;
+  for (int b = 0; b < 2; b++) { a.base[b] = pix == 4 ? p->d_base_rgba[b] : p->d_base_gray[b]; a.base_out[b] = 0; }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
   int smem_total, tx = 1, ty = 1;
   if (mode == TBX_OBS_GRAY_AREA) {
     AreaRes *ar = 0;
     r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
-    a.base_out = ar->d_base_out; a.plan = ar->d_plan;
+    a.base_out[0] = ar->d_base_out[0]; a.base_out[1] = ar->d_base_out[1]; a.plan = ar->d_plan;
     a.band_rows = H;
     tx = ar->tx; ty = ar->ty;
     /* surplus (zero-weight) taps may read up to TY-1 rows past the canvas: keep them inside the allocation */
     const int ty_inst = (tx > 5 || ty > 4) ? 8 : (ty <= 3 ? 3 : 4);
-    a.smem_out = a.smem_canvas + align16(W * H + (ty_inst - 1) * W + 16);
-    a.smem_rects = a.smem_out + 2 * align16(out_w * out_h);
-    a.smem_plan = 0;
-    smem_total = a.smem_rects + TBX_MAX_RECTS * (int)sizeof(int4) + 16;
+    a.smem_rects = a.smem_canvas + align16(W * H + (ty_inst - 1) * W + 16);
   } else {
-    /* canvas bands of at most ~48 KB so several CTAs stay resident per SM */
-    int max_rows = (48 * 1024) / (W * pix);
+    /* canvas bands of at most ~40 KB so that five CTAs stay resident per SM */
+    int max_rows = (40 * 1024) / (W * pix);
     if (max_rows < 1) max_rows = 1;
     int nb = (H + max_rows - 1) / max_rows;
     a.band_rows = (H + nb - 1) / nb;
-    a.smem_out = a.smem_plan = a.smem_rects = 0;
-    smem_total = a.smem_canvas + align16(a.band_rows * W * pix);
+    a.smem_rects = a.smem_canvas + align16(a.band_rows * W * pix);
   }
+  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 16;
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
   if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, smem_total, s);
@@ -514,7 +518,7 @@ int tbx_state_from_json(tbx_pool *p, const int32_t *ids, int n, const char *cons
     for (int i = 0; i < n; i++) {
       uint32_t *R = recs.data() + (size_t)i * rw;
       Value v = tbxjson::parse(json[i]);
-      if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_state_from_json(v, *reinterpret_cast<BrkRec *>(R), t); new_brk.push_back(t); }
+      if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_state_from_json(v, *reinterpret_cast<BrkRec *>(R), t); tbx::brk_mark_delta_ok(p->cfg, t); new_brk.push_back(t); }
       else if (p->game == TBX_AMIDAR) { AmiTable t; tbx::ami_state_from_json(v, *reinterpret_cast<AmiRec *>(R), t); new_ami.push_back(t); }
       else tbx::si_state_from_json(v, *reinterpret_cast<SiRec *>(R));
     }

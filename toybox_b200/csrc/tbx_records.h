@@ -56,7 +56,8 @@ typedef struct {
 
 typedef struct {
   int32_t n_bricks, disjoint; /* disjoint: no two brick rects overlap -> they may be painted in any order */
-  int32_t hud_clear, _pad;    /* no brick rect reaches into the HUD digit rows (y < 12) */
+  int32_t hud_clear;          /* no brick rect reaches into the HUD digit rows (y < 12) */
+  int32_t delta_ok;           /* disjoint, HUD-clear and every brick lies on pure background: base frame 1 may hold them */
   double bb_x0, bb_y0, bb_x1, bb_y1; /* union of all brick boxes (collision early-out) */
   double px[TBX_BRK_MAX_BRICKS], py[TBX_BRK_MAX_BRICKS], sx[TBX_BRK_MAX_BRICKS], sy[TBX_BRK_MAX_BRICKS];
   double x1[TBX_BRK_MAX_BRICKS], y1[TBX_BRK_MAX_BRICKS]; /* px+sx, py+sy (same IEEE add the step does) */

@@ -1,19 +1,22 @@
 /* tbx_render.cuh -- the render kernel (Toybox.get_state / get_rgb_frame for a whole pool; fused WarpFrame).
  *
- * One CTA renders a chunk of TBX_EPC = 8 consecutive envs (8 envs x 4 B = one 32-byte sector per state word, so
- * the word-major planes are read at full sector efficiency).  Per env:
- *   1. the STATIC part of the frame (config-only draw-list slots: walls, ground line) is not painted at all:
- *      a pre-rendered base canvas (and, for the INTER_AREA layout, its pre-computed down-sample) is copied in
- *      from L2;
- *   2. the dynamic draw list is built straight from the env's record and painted into the shared-memory canvas
- *      group by group, in draw order.  Inside a group whose primitives cannot conflict (disjoint or same colour)
- *      every thread paints its own small rectangle with 32-bit span stores and larger / masked primitives are
- *      painted warp-cooperatively; groups that may conflict are painted by one warp, strictly in order.  The
- *      result equals the painter's algorithm over the whole draw list;
- *   3. native layouts (RGBA / RGB / gray) stream the canvas band to HBM with 16-byte coalesced stores;
- *      the INTER_AREA layout recomputes only the output pixels whose taps touch a dynamic primitive (dirty
- *      rectangles tracked while painting), with the exact f32 tap order of cv2's area resize, patches them
- *      into the staged base output and streams the 84x84 frame out with 16-byte stores.
+ * DELTA RENDERING over a persistent shared-memory canvas.  One CTA owns a band of canvas rows and renders it for a
+ * chunk of TBX_EPC = 8 consecutive envs (8 envs x 4 B = one 32-byte sector per state word, so the word-major
+ * planes are read at full sector efficiency).
+ *   - The canvas is initialised ONCE per CTA from a pre-rendered BASE FRAME of the pool's config (base 0: static
+ *     draw-list slots -- walls, ground line; base 1: plus the look of a fresh game -- all bricks / the config's
+ *     tile board), kept in L2.
+ *   - Per env only the draw-list entries that differ from the base are built (straight from the env's record)
+ *     and painted, group by group in draw order.  Inside a group whose primitives cannot conflict (disjoint, or
+ *     one colour) every thread paints its own small rectangle with 32-bit span stores, larger / sprite-masked
+ *     primitives are painted warp-cooperatively; groups that may conflict are painted by one warp strictly in
+ *     order.  The result equals the painter's algorithm over the full draw list.  Painted areas are recorded as
+ *     dirty rectangles.
+ *   - Native layouts (RGBA / RGB / gray) stream the canvas band to HBM with 16-byte coalesced streaming stores.
+ *     The INTER_AREA layout copies the pre-computed down-sample of the base frame to the destination and then
+ *     recomputes only the output pixels whose taps touch a dirty rectangle, with cv2's exact f32 tap order.
+ *   - Afterwards the dirty rectangles are restored from the base frame, so per-env work is proportional to what
+ *     differs from the base, not to the frame size.
  */
 #ifndef TBX_RENDER_CUH
 #define TBX_RENDER_CUH
@@ -32,8 +35,7 @@ namespace tbxk {
 #endif
 #define TBX_RENDER_WARPS (TBX_RENDER_THREADS / 32)
 #define TBX_EPC 8
-#define TBX_MAX_GROUPS 4
-#define TBX_MAX_RECTS (TBX_MAX_GROUPS + 32)
+#define TBX_MAX_RECTS 96
 
 __device__ const uint32_t d_bank[TBX_BANK_WORDS] = TBX_BANK_INIT;
 
@@ -43,8 +45,8 @@ template <> struct Traits<TBX_BREAKOUT> {
   static constexpr int W = TBX_BRK_W, H = TBX_BRK_H, NS = BRK_N_SLOTS, RW = TBX_WORDS(BrkRec), NG = BRK_N_GROUPS;
   static __device__ __forceinline__ void step(const TbxAcc &S, const Cfg &c, const Table *t, int in) { brk_step(S, c, t, in); }
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *) { brk_new_game(S, c); }
-  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s) { return brk_prim(R, c, t, s); }
-  static __device__ __forceinline__ uint32_t clear_color(const Cfg &c) { return c.bg_color; }
+  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return brk_prim_delta(R, c, t, s, base); }
+  static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return brk_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int &b, int &e, int &mode) { brk_group(g, R, t, b, e, mode); }
 };
 template <> struct Traits<TBX_SPACE_INVADERS> {
@@ -52,8 +54,8 @@ template <> struct Traits<TBX_SPACE_INVADERS> {
   static constexpr int W = TBX_SI_W, H = TBX_SI_H, NS = SI_N_SLOTS, RW = TBX_WORDS(SiRec), NG = SI_N_GROUPS;
   static __device__ __forceinline__ void step(const TbxAcc &S, const Cfg &c, const Table *, int in) { si_step(S, c, in); }
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *) { si_new_game(S, c); }
-  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &, const Table *, int s) { return si_prim(R, s); }
-  static __device__ __forceinline__ uint32_t clear_color(const Cfg &) { return SI_COLOR_BLACK; }
+  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &, const Table *, int s, int) { return si_prim(R, s); }
+  static __device__ __forceinline__ int base_id(const uint32_t *, const Cfg &, const Table *) { return 0; }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
 };
 template <> struct Traits<TBX_AMIDAR> {
@@ -61,8 +63,8 @@ template <> struct Traits<TBX_AMIDAR> {
   static constexpr int W = TBX_AMI_W, H = TBX_AMI_H, NS = AMI_N_SLOTS, RW = TBX_WORDS(AmiRec), NG = AMI_N_GROUPS;
   static __device__ __forceinline__ void step(const TbxAcc &S, const Cfg &c, const Table *t, int in) { ami_step(S, c, t, in); }
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *t) { ami_new_game(S, c, t); }
-  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s) { return ami_prim(R, c, t, s); }
-  static __device__ __forceinline__ uint32_t clear_color(const Cfg &c) { return c.bg_color; }
+  static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return ami_prim_delta(R, c, t, s, base); }
+  static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return ami_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int &b, int &e, int &mode) { ami_group(g, b, e, mode); }
 };
 
@@ -72,11 +74,11 @@ struct RenderArgs {
   const void *cfg, *tables;
   uint8_t *dst;
   size_t frame_bytes;
-  const uint8_t *base;     /* static frame: gray bytes (gray layouts) or RGBA (colour layouts) */
-  const uint8_t *base_out; /* INTER_AREA: down-sample of the static frame */
-  const TbxAreaPlan *plan; /* INTER_AREA */
-  int band_rows;           /* native layouts: canvas rows per pass */
-  int smem_canvas, smem_out, smem_plan, smem_rects; /* byte offsets into dynamic shared memory */
+  const uint8_t *base[2];     /* base frames 0/1: gray bytes (gray layouts) or RGBA (colour layouts) */
+  const uint8_t *base_out[2]; /* INTER_AREA: their down-samples */
+  const TbxAreaPlan *plan;    /* INTER_AREA */
+  int band_rows;              /* canvas rows per CTA (blockIdx.y selects the band) */
+  int smem_canvas, smem_rects; /* byte offsets into dynamic shared memory */
 };
 
 template <int PIX> struct PixT;
@@ -93,15 +95,17 @@ template <int W> __device__ __forceinline__ bool clip_prim(const TbxPrim &p, int
 /* one thread fills a small solid rectangle: aligned 32-bit span stores for the 1-byte canvas */
 template <int PIX, int W>
 __device__ __forceinline__ void paint_small(typename PixT<PIX>::T *canvas, int r0, const Clip &c, uint32_t val) {
-  for (int y = c.y0; y < c.y1; y++) {
-    if (PIX == 1) {
+  if (PIX == 1) {
+    const uint32_t v4 = (val & 255u) * 0x01010101u;
+    const int xa = min((c.x0 + 3) & ~3, c.x1), xb = max(c.x1 & ~3, xa);
+    for (int y = c.y0; y < c.y1; y++) {
       uint8_t *row = reinterpret_cast<uint8_t *>(canvas) + (size_t)(y - r0) * W;
-      const uint32_t v4 = (val & 255u) * 0x01010101u;
-      int x = c.x0;
-      for (; x < c.x1 && (x & 3); x++) row[x] = (uint8_t)val;
-      for (; x + 4 <= c.x1; x += 4) *reinterpret_cast<uint32_t *>(row + x) = v4;
-      for (; x < c.x1; x++) row[x] = (uint8_t)val;
-    } else {
+      for (int x = c.x0; x < xa; x++) row[x] = (uint8_t)val;
+      for (int x = xa; x < xb; x += 4) *reinterpret_cast<uint32_t *>(row + x) = v4;
+      for (int x = xb; x < c.x1; x++) row[x] = (uint8_t)val;
+    }
+  } else {
+    for (int y = c.y0; y < c.y1; y++) {
       uint32_t *row = reinterpret_cast<uint32_t *>(canvas) + (size_t)(y - r0) * W;
       for (int x = c.x0; x < c.x1; x++) row[x] = val;
     }
@@ -134,37 +138,35 @@ __device__ __forceinline__ void paint_coop(typename PixT<PIX>::T *canvas, int r0
   }
 }
 
-/* warp-wide bounding box of the lanes' clipped rectangles (hardware integer warp reductions) */
-__device__ __forceinline__ int4 warp_bbox(int bx0, int by0, int bx1, int by1) {
-  return make_int4(__reduce_min_sync(0xffffffffu, bx0), __reduce_min_sync(0xffffffffu, by0), __reduce_max_sync(0xffffffffu, bx1),
-                   __reduce_max_sync(0xffffffffu, by1));
+/* dirty-rectangle list: rects[0..min(*n, TBX_MAX_RECTS)); *n > TBX_MAX_RECTS means "overflowed: everything is dirty" */
+__device__ __forceinline__ void push_rect(int4 *rects, int *n, int4 r) {
+  int slot = atomicAdd(n, 1);
+  if (slot < TBX_MAX_RECTS) rects[slot] = r;
 }
 
-/* Paint every dynamic draw-list group of one env into canvas rows [r0,r1), in draw order.  When `rects` is given
- * the dirty rectangles (native coordinates) are appended to it: one bounding box per group, except that an in-order
- * group of at most 32 slots contributes one rectangle per primitive (a ball far from the paddle must not dirty
- * everything in between).  All threads of the CTA must call this; it ends with a barrier. */
+/* Paint every draw-list group of one env that differs from base frame `base` into canvas rows [r0,r1), in draw
+ * order, and append the painted areas to the dirty list: one bounding box per warp pass of a parallel group (32
+ * consecutive slots are spatially close: brick columns, a tile row), one rectangle per primitive of the in-order
+ * group.  All threads of the CTA must call this; it ends with a barrier. */
 template <int GAME, int PIX>
 __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
-                                          typename PixT<PIX>::T *canvas, int r0, int r1, int4 *rects, int *n_rects) {
+                                          int base, typename PixT<PIX>::T *canvas, int r0, int r1, int4 *rects, int *n_rects) {
   typedef Traits<GAME> T;
   constexpr int W = T::W;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int g = 0; g < T::NG; g++) {
     int gb, ge, gmode;
     T::group(g, R, tables, gb, ge, gmode);
-    if (gb >= ge) continue; /* empty group (merged into its neighbour): uniform across the CTA, no barrier */
+    if (gb >= ge) continue; /* uniform across the CTA */
     if (!(gmode & TBX_GROUP_SERIAL)) {
-      int bx0 = 32767, by0 = 32767, bx1 = -1, by1 = -1;
       for (int s0 = gb; s0 < ge; s0 += TBX_RENDER_THREADS) {
         const int s = s0 + tid;
         TbxPrim p = tbx_prim_none();
-        if (s < ge) p = T::prim(R, cfg, tables, s);
+        if (s < ge) p = T::prim(R, cfg, tables, s, base);
         Clip c;
         const bool ok = clip_prim<W>(p, r0, r1, c);
         if (!__any_sync(0xffffffffu, ok)) continue;
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
-        if (ok) { bx0 = min(bx0, c.x0); by0 = min(by0, c.y0); bx1 = max(bx1, c.x1); by1 = max(by1, c.y1); }
         const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 96;
         if (small) paint_small<PIX, W>(canvas, r0, c, val);
         unsigned big = __ballot_sync(0xffffffffu, ok && !small);
@@ -183,26 +185,27 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
             paint_coop<PIX, W>(canvas, r0, qc, q.x, q.y, qv, q3, R, lane);
           }
         }
-      }
-      if (rects && __any_sync(0xffffffffu, bx1 > bx0)) {
-        const int4 bb = warp_bbox(bx0, by0, bx1, by1);
-        if (lane == 0) { atomicMin(&rects[g].x, bb.x); atomicMin(&rects[g].y, bb.y); atomicMax(&rects[g].z, bb.z); atomicMax(&rects[g].w, bb.w); }
+        /* this warp pass's bounding box (hardware integer warp reductions) */
+        const int bx0 = __reduce_min_sync(0xffffffffu, ok ? c.x0 : 32767), by0 = __reduce_min_sync(0xffffffffu, ok ? c.y0 : 32767);
+        const int bx1 = __reduce_max_sync(0xffffffffu, ok ? c.x1 : -1), by1 = __reduce_max_sync(0xffffffffu, ok ? c.y1 : -1);
+        if (lane == 0) push_rect(rects, n_rects, make_int4(bx0, by0, bx1, by1));
       }
     } else if (wid == 0) {
       /* in order: lane l builds primitive gb + 32*batch + l, then the warp paints them one at a time */
-      int bx0 = 32767, by0 = 32767, bx1 = -1, by1 = -1;
-      const bool per_prim_rects = (ge - gb) <= 32;
       for (int s0 = gb; s0 < ge; s0 += 32) {
         const int s = s0 + lane;
         TbxPrim p = tbx_prim_none();
-        if (s < ge) p = T::prim(R, cfg, tables, s);
+        if (s < ge) p = T::prim(R, cfg, tables, s, base);
         Clip c;
         const bool ok = clip_prim<W>(p, r0, r1, c);
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
-        if (ok) { bx0 = min(bx0, c.x0); by0 = min(by0, c.y0); bx1 = max(bx1, c.x1); by1 = max(by1, c.y1); }
         unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (rects && per_prim_rects && ok) rects[T::NG + __popc(m & ((1u << lane) - 1u))] = make_int4(c.x0, c.y0, c.x1, c.y1);
-        if (rects && per_prim_rects && lane == 0) *n_rects = T::NG + __popc(m);
+        if (m == 0) continue;
+        int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(n_rects, __popc(m));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
+        if (ok && slot < TBX_MAX_RECTS) rects[slot] = make_int4(c.x0, c.y0, c.x1, c.y1);
         const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
         const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
         while (m) {
@@ -218,12 +221,36 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
           __syncwarp();
         }
       }
-      if (rects && !per_prim_rects) {
-        const int4 bb = warp_bbox(bx0, by0, bx1, by1);
-        if (lane == 0 && bb.z > bb.x) rects[g] = bb;
-      }
     }
     if (!(gmode & TBX_GROUP_NOSYNC)) __syncthreads();
+  }
+}
+
+/* copy rows [r0,r1) of a base frame into the canvas (full initialisation) */
+template <int PIX, int W>
+__device__ __forceinline__ void load_canvas(typename PixT<PIX>::T *canvas, const uint8_t *base, int r0, int r1) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)r0 * W * PIX);
+  uint4 *dst = reinterpret_cast<uint4 *>(canvas);
+  const int n16 = (r1 - r0) * W * PIX / 16;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
+}
+/* undo one env's painting: re-copy the dirty rectangles (whole 16-byte chunks) from the base frame */
+template <int PIX, int W>
+__device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, const uint8_t *base, int r0, int r1, const int4 *rects, int n) {
+  if (n > TBX_MAX_RECTS) { load_canvas<PIX, W>(canvas, base, r0, r1); return; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = wid; i < n; i += TBX_RENDER_WARPS) {
+    const int4 rc = rects[i];
+    if (rc.z <= rc.x) continue;
+    const int b0 = (rc.x * PIX) & ~15, b1 = (rc.z * PIX + 15) & ~15, nch = (b1 - b0) >> 4;
+    const int cnt = nch * (rc.w - rc.y);
+    const float inv = 1.0f / (float)nch;
+    for (int k = lane; k < cnt; k += 32) {
+      const int yy = (int)(((float)k + 0.5f) * inv), ch = k - yy * nch;
+      const size_t off = (size_t)(rc.y + yy) * W * PIX + b0 + 16 * ch;
+      *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(canvas) + off - (size_t)r0 * W * PIX) = __ldg(reinterpret_cast<const uint4 *>(base + off));
+    }
   }
 }
 
@@ -239,135 +266,136 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
   uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
   uint32_t *recs = reinterpret_cast<uint32_t *>(smem);
   P *canvas = reinterpret_cast<P *>(smem + a.smem_canvas);
+  int4 *rect_buf = reinterpret_cast<int4 *>(smem + a.smem_rects); /* two lists, used alternately */
+  int *rect_n = reinterpret_cast<int *>(rect_buf + 2 * TBX_MAX_RECTS);
   const typename T::Cfg &cfg = *(const typename T::Cfg *)a.cfg;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
   const int ne = min(TBX_EPC, a.n - e0);
+  const int r0 = MODE == 3 ? 0 : blockIdx.y * a.band_rows, r1 = MODE == 3 ? H : min(H, r0 + a.band_rows);
 
   /* coalesced load of the chunk's state words: thread -> (word, env) with env fastest */
   for (int i = tid; i < RW * TBX_EPC; i += TBX_RENDER_THREADS) {
     int w = i / TBX_EPC, j = i - w * TBX_EPC;
     if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
   }
+  if (tid < 2) rect_n[tid] = 0;
+  __syncthreads();
 
-  if (MODE != 3) {
-    __syncthreads();
+  if constexpr (MODE == 3) {
+    /* the static part of every output frame of the chunk: the base frame's down-sample, global -> global */
+    const TbxAreaPlan *__restrict__ plan = a.plan;
+    const int nout16 = (int)(a.frame_bytes >> 4);
+    for (int j = 0; j < ne; j++) {
+      const uint4 *src = reinterpret_cast<const uint4 *>((T::base_id(recs + j * RW, cfg, tables) ? a.base_out[1] : a.base_out[0]));
+      uint4 *dst = reinterpret_cast<uint4 *>(a.dst + (size_t)(e0 + j) * a.frame_bytes);
+      if ((a.frame_bytes & 15) == 0) {
+        for (int i = tid; i < nout16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i); /* stays in L2 until patched below */
+      } else {
+        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src);
+        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
+        for (int i = tid; i < (int)a.frame_bytes; i += TBX_RENDER_THREADS) d8[i] = s8[i];
+      }
+    }
+    const int dw = plan->dw;
+    int canvas_base = -1;
     for (int j = 0; j < ne; j++) {
       const uint32_t *R = recs + j * RW;
+      const int base = T::base_id(R, cfg, tables);
+      int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
+      int *n_rects = rect_n + (j & 1);
+      /* bring the canvas back to the base frame (the barrier after the previous env's recompute precedes this) */
+      if (canvas_base != base) load_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), 0, H);
+      else restore_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), 0, H, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
+      canvas_base = base;
+      __syncthreads();
+      if (tid == 0) rect_n[(j - 1) & 1] = 0; /* that list is reused by env j+1 */
+      paint_env<GAME, 1>(R, cfg, tables, base, canvas, 0, H, rects, n_rects);
+      /* Recompute the output pixels fed by a dirty rectangle and patch them into the destination frame (the
+       * barriers inside paint_env order these byte stores after the frame's base copy above).  Lanes own output
+       * columns (their taps stay in registers), warps own output rows; narrow rectangles pack several rows into
+       * one warp.  Straight-line TX x TY taps, surplus taps carry zero weights (x + 0*b == x for these sums). */
       uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
-      for (int r0 = 0; r0 < H; r0 += a.band_rows) {
-        const int r1 = min(H, r0 + a.band_rows);
-        const int n16 = (r1 - r0) * W * PIX / 16;
-        {
-          const uint4 *src = reinterpret_cast<const uint4 *>(a.base + (size_t)r0 * W * PIX);
-          uint4 *dst = reinterpret_cast<uint4 *>(canvas);
-          for (int i = tid; i < n16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();
-        paint_env<GAME, PIX>(R, cfg, tables, canvas, r0, r1, (int4 *)0, (int *)0);
-        if (MODE == 1) {
-          /* 16 pixels (64 B of RGBA) -> 48 B of RGB, three 16-byte stores per thread */
-          const int groups = (r1 - r0) * W / 16;
-          const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
-          uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * 3);
-          for (int g = tid; g < groups; g += TBX_RENDER_THREADS) {
-            uint32_t p[16];
+      int nr = *n_rects;
+      const bool overflow = nr > TBX_MAX_RECTS;
+      if (overflow) nr = 1;
+      for (int r = 0; r < nr; r++) {
+        const int4 rc = overflow ? make_int4(0, 0, W, H) : rects[r];
+        if (rc.z <= rc.x) continue;
+        const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
+        const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
+        const int ncols = dx1 - dx0 + 1;
+        const int lg = ncols > 16 ? 5 : ncols > 8 ? 4 : ncols > 4 ? 3 : 2; /* columns per warp pass = 1 << lg */
+        const int cpl = 1 << lg, rpi = 32 >> lg, sub = lane >> lg, c = lane & (cpl - 1);
+        for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
+          const bool colok = dxb + c <= dx1;
+          const int dx = colok ? dxb + c : dx1;
+          const uint8_t *col = reinterpret_cast<const uint8_t *>(canvas) + __ldg(&plan->xs0[dx]);
+          float al[TX];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { uint4 v = src[g * 4 + k]; p[4 * k] = v.x; p[4 * k + 1] = v.y; p[4 * k + 2] = v.z; p[4 * k + 3] = v.w; }
-            uint32_t o[12];
+          for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+          for (int dy = dy0 + wid * rpi + sub; dy <= dy1; dy += TBX_RENDER_WARPS * rpi) {
+            const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
+            float v = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 4; k++) { /* 4 pixels -> 3 words */
-              uint32_t c0 = p[4 * k] & 0xffffffu, c1 = p[4 * k + 1] & 0xffffffu, c2 = p[4 * k + 2] & 0xffffffu, c3 = p[4 * k + 3] & 0xffffffu;
-              o[3 * k] = c0 | (c1 << 24);
-              o[3 * k + 1] = (c1 >> 8) | (c2 << 16);
-              o[3 * k + 2] = (c2 >> 16) | (c3 << 8);
+            for (int k = 0; k < TY; k++) {
+              float h = tbx_fmul((float)row[k * W], al[0]);
+#pragma unroll
+              for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[k * W + t], al[t]));
+              const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+              v = k == 0 ? bh : tbx_fadd(v, bh);
             }
-            __stcs(dst + g * 3, make_uint4(o[0], o[1], o[2], o[3]));
-            __stcs(dst + g * 3 + 1, make_uint4(o[4], o[5], o[6], o[7]));
-            __stcs(dst + g * 3 + 2, make_uint4(o[8], o[9], o[10], o[11]));
+            const int iv = tbx_f2i_rn(v);
+            if (colok) out[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
           }
-        } else {
-          const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
-          uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * PIX);
-          for (int i = tid; i < n16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
         }
-        __syncthreads();
       }
+      __syncthreads(); /* the canvas is restored next */
     }
     return;
   }
 
-  /* ---- INTER_AREA layout.  The staged output is double-buffered so that streaming frame j out overlaps with
-   * staging the base frame for env j+1 (one barrier fewer per env). */
-  const TbxAreaPlan *__restrict__ plan = a.plan; /* read through L1: small, shared by every CTA */
-  int4 *rects = reinterpret_cast<int4 *>(smem + a.smem_rects);
-  int *n_rects = reinterpret_cast<int *>(rects + TBX_MAX_RECTS);
-  const int dw = plan->dw, dh = plan->dh;
-  const int nout16 = (dw * dh + 15) / 16;
-  const int ostage_bytes = nout16 * 16;
-  for (int j = 0; j <= ne; j++) {
-    if (j > 0) { /* stream frame j-1 out */
-      const uint8_t *ostage = smem + a.smem_out + ((j - 1) & 1) * ostage_bytes;
-      uint8_t *out = a.dst + (size_t)(e0 + j - 1) * a.frame_bytes;
-      if ((a.frame_bytes & 15) == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(ostage);
-        uint4 *dst = reinterpret_cast<uint4 *>(out);
-        for (int i = tid; i < dw * dh / 16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
-      } else {
-        for (int i = tid; i < dw * dh; i += TBX_RENDER_THREADS) out[i] = ostage[i];
-      }
-    }
-    if (j == ne) break;
+  /* ---- native layouts: stream the band out, env after env */
+  int canvas_base = -1;
+  for (int j = 0; j < ne; j++) {
     const uint32_t *R = recs + j * RW;
-    uint8_t *ostage = smem + a.smem_out + (j & 1) * ostage_bytes;
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(a.base);
-      uint4 *dst = reinterpret_cast<uint4 *>(canvas);
-#pragma unroll 4
-      for (int i = tid; i < W * H / 16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
-      const uint4 *src2 = reinterpret_cast<const uint4 *>(a.base_out);
-      uint4 *dst2 = reinterpret_cast<uint4 *>(ostage);
-      for (int i = tid; i < nout16; i += TBX_RENDER_THREADS) dst2[i] = __ldg(src2 + i);
-      if (tid < T::NG) rects[tid] = make_int4(32767, 32767, -1, -1);
-      if (tid == 0) *n_rects = T::NG;
-    }
+    const int base = T::base_id(R, cfg, tables);
+    int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
+    int *n_rects = rect_n + (j & 1);
+    if (canvas_base != base) load_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
+    else restore_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
+    canvas_base = base;
     __syncthreads();
-    paint_env<GAME, 1>(R, cfg, tables, reinterpret_cast<uint8_t *>(canvas), 0, H, rects, n_rects);
-    /* recompute the output pixels fed by a dirty rectangle.  Lanes own output columns (their taps stay in
-     * registers), warps own output rows; narrow rectangles pack several rows into one warp.  The tap loops are
-     * straight-line: TX x TY taps, surplus taps carry zero weights (x + 0*b == x exactly for these sums). */
-    const int nr = *n_rects;
-    for (int r = 0; r < nr; r++) {
-      const int4 rc = rects[r];
-      if (rc.z <= rc.x) continue;
-      const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
-      const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
-      const int ncols = dx1 - dx0 + 1;
-      const int lg = ncols > 16 ? 5 : ncols > 8 ? 4 : ncols > 4 ? 3 : 2; /* columns per warp pass = 1 << lg */
-      const int cpl = 1 << lg, rpi = 32 >> lg, sub = lane >> lg, c = lane & (cpl - 1);
-      for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
-        const bool colok = dxb + c <= dx1;
-        const int dx = colok ? dxb + c : dx1;
-        const uint8_t *col = reinterpret_cast<const uint8_t *>(canvas) + __ldg(&plan->xs0[dx]);
-        float al[TX];
+    if (tid == 0) rect_n[(j - 1) & 1] = 0;
+    paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
+    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    if (MODE == 1) {
+      /* 16 pixels (64 B of RGBA) -> 48 B of RGB, three 16-byte stores per thread */
+      const int groups = (r1 - r0) * W / 16;
+      const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * 3);
+      for (int g = tid; g < groups; g += TBX_RENDER_THREADS) {
+        uint32_t p[16];
 #pragma unroll
-        for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
-        for (int dy = dy0 + wid * rpi + sub; dy <= dy1; dy += TBX_RENDER_WARPS * rpi) {
-          const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
-          float v = 0.0f;
+        for (int k = 0; k < 4; k++) { uint4 v = src[g * 4 + k]; p[4 * k] = v.x; p[4 * k + 1] = v.y; p[4 * k + 2] = v.z; p[4 * k + 3] = v.w; }
+        uint32_t o[12];
 #pragma unroll
-          for (int k = 0; k < TY; k++) {
-            float h = tbx_fmul((float)row[k * W], al[0]);
-#pragma unroll
-            for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[k * W + t], al[t]));
-            const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
-            v = k == 0 ? bh : tbx_fadd(v, bh);
-          }
-          const int iv = tbx_f2i_rn(v);
-          if (colok) ostage[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        for (int k = 0; k < 4; k++) { /* 4 pixels -> 3 words (byte permutes) */
+          o[3 * k] = __byte_perm(p[4 * k], p[4 * k + 1], 0x4210);
+          o[3 * k + 1] = __byte_perm(p[4 * k + 1], p[4 * k + 2], 0x5421);
+          o[3 * k + 2] = __byte_perm(p[4 * k + 2], p[4 * k + 3], 0x6542);
         }
+        __stcs(dst + g * 3, make_uint4(o[0], o[1], o[2], o[3]));
+        __stcs(dst + g * 3 + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        __stcs(dst + g * 3 + 2, make_uint4(o[8], o[9], o[10], o[11]));
       }
+    } else {
+      const int n16 = (r1 - r0) * W * PIX / 16;
+      const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * PIX);
+#pragma unroll 4
+      for (int i = tid; i < n16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
     }
     __syncthreads();
   }
