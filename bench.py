@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--obs", default="gray84")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--policy", default="random", choices=["random", "track"],
+                    help="random = the headline uniform stream; track = scripted Breakout ball tracking (breaks bricks)")
+    ap.add_argument("--presteps", type=int, default=0, help="untimed step-only frames before the warm-up")
     return ap.parse_args()
 
 
@@ -163,8 +166,14 @@ def main():
     actions = torch.empty(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    def fill(t):
+        if args.policy == "track":
+            pool.fill_policy_actions(actions, 1, t)
+        else:
+            pool.fill_random_actions(actions, ACTION_SEED, t, env0)
+
     def step(t, ev=None):
-        pool.fill_random_actions(actions, ACTION_SEED, t, env0)
+        fill(t)
         if ev is not None:
             ev[0].record(stream)
         pool.apply_ale_action(actions, auto_reset=True)
@@ -175,6 +184,10 @@ def main():
             ev[2].record(stream)
 
     t = 0
+    for _ in range(args.presteps):          # advance the games without rendering (untimed) to reach mid-game states
+        fill(t)
+        pool.apply_ale_action(actions, auto_reset=True)
+        t += 1
     for _ in range(max(args.warmup, 3)):
         step(t)
         t += 1
@@ -275,7 +288,8 @@ def main():
         "config": {"workload": workload_name(args.game, n, args.obs), "envs_per_gpu": n, "obs_bytes_per_env": fb,
                    "l2": "each step writes %d MB of observations (> 126 MB L2) between reuses of the %d MB state" %
                          (n * fb // 2 ** 20, n * rec_bytes // 2 ** 20),
-                   "seeds": "env i: set_seed(1234+i); actions: counter-based stream seed 0xB200"},
+                   "seeds": "env i: set_seed(1234+i); actions: counter-based stream seed 0xB200",
+                   "policy": args.policy, "presteps": args.presteps},
         "frames_per_sec": value, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
         "launches_per_step": ["fill_actions_kernel", "step_kernel", "render_kernel"],
         "clocks": clocks, "episode_stats": {"episodes": stats[0], "sum_return": stats[1], "sum_length": stats[2], "max_return": stats[3]},

@@ -121,6 +121,11 @@ int tbx_stats_read(tbx_pool *pool, int64_t *out_host, int reset, void *stream);
  * legal[index(seed, env0 + i, t)] for the pool's game (counter-based, reproducible on the CPU). */
 int tbx_fill_actions(tbx_pool *pool, int32_t *actions_dev, uint64_t seed, uint64_t env0, uint64_t t, void *stream);
 
+/* Benchmark utility: scripted actions computed on the device from the envs' own state.  policy 1 = Breakout
+ * "track the ball" (FIRE to serve, then follow the first ball with a varying aim offset), which drives games deep
+ * into the brick wall -- states the uniform random stream almost never reaches. */
+int tbx_fill_actions_policy(tbx_pool *pool, int32_t *actions_dev, int policy, uint64_t t, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

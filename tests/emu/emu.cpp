@@ -148,10 +148,11 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
   int covered = tbx::n_static_slots(e->game);
   for (int g = 0; g < ng; g++) {
     int gb, ge, mode;
-    if (e->game == TBX_BREAKOUT) brk_group(g, e->rec.data(), e->brk_tables.data(), gb, ge, mode);
+    if (e->game == TBX_BREAKOUT) brk_group(g, e->rec.data(), e->brk_tables.data(), base_id, gb, ge, mode);
     else if (e->game == TBX_AMIDAR) ami_group(g, gb, ge, mode);
     else si_group(g, gb, ge, mode);
-    if (gb != covered) { g_err = "groups do not tile the dynamic slots"; return -1; }
+    if (gb != covered && gb < ge) { g_err = "groups do not tile the dynamic slots"; return -1; }
+    if (gb >= ge) { covered = e->game == TBX_BREAKOUT && g == 1 ? BRK_SLOT_PADDLE : covered; continue; } /* skipped group */
     covered = ge;
     Rect box = {32767, 32767, -1, -1};
     const bool per_prim = (mode & TBX_GROUP_SERIAL) && ge - gb <= 32;

@@ -28,7 +28,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + [os.path.join(_CSRC, s) for s in SOURCES]
+    extra = os.environ.get("TBX_NVCC_EXTRA", "").split()          # tuning experiments, e.g. -DTBX_RENDER_THREADS=128
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + [os.path.join(_CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return _SO
 
@@ -75,6 +76,7 @@ def lib():
         "tbx_free_str": (None, [vp]),
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
+        "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)          # AttributeError here = the header and the library disagree
@@ -88,7 +90,7 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_n_envs", "tbx_device", "tbx_legal_actions", "tbx_obs_bytes", "tbx_seed", "tbx_new_game", "tbx_step",
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
-           "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions"]
+           "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy"]
 
 
 def check(rc):

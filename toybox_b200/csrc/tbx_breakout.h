@@ -30,10 +30,17 @@
 #define BRK_N_STATIC 3 /* leading slots that depend on the config only */
 #define BRK_N_GROUPS 3
 /* HUD digits (one colour) | bricks (parallel iff the table's rectangles are disjoint) | paddle, balls (in order) */
-TBX_HD void brk_group(int g, const uint32_t *R, const BrkTable *tables, int &b, int &e, int &mode) {
+TBX_HD void brk_group(int g, const uint32_t *R, const BrkTable *tables, int base, int &b, int &e, int &mode) {
   const BrkTable &T = tables[(int32_t)R[TBX_W(TbxHdr, tbl)]];
   if (g == 0) { b = BRK_SLOT_SCORE; e = BRK_SLOT_BRICKS; mode = TBX_GROUP_PARALLEL | (T.hud_clear ? TBX_GROUP_NOSYNC : 0); }
-  else if (g == 1) { b = BRK_SLOT_BRICKS; e = BRK_SLOT_PADDLE; mode = T.disjoint ? TBX_GROUP_PARALLEL : TBX_GROUP_SERIAL; }
+  else if (g == 1) {
+    b = BRK_SLOT_BRICKS; e = BRK_SLOT_PADDLE; mode = T.disjoint ? TBX_GROUP_PARALLEL : TBX_GROUP_SERIAL;
+    if (base == 1) { /* delta rendering: nothing to paint while every brick is alive */
+      uint32_t dead = 0;
+      for (int k = 0; k < 5; k++) dead |= T.all_mask[k] & ~R[TBX_W(BrkRec, alive) + k];
+      if (!dead) e = b;
+    }
+  }
   else { b = BRK_SLOT_PADDLE; e = BRK_N_SLOTS; mode = TBX_GROUP_SERIAL; }
 }
 

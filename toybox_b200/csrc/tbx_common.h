@@ -243,10 +243,12 @@ TBX_HD bool tbx_prim_covers(const TbxPrim &p, const uint32_t *bank, const uint32
 /* right-aligned decimal digits as sprite prims: slot k (0 = least significant) of at most `max_digits`;
  * mirrors the HUD digit layout of the draw lists (3x5 font, 1 column gap) */
 TBX_HD TbxPrim tbx_prim_digit(uint32_t color, int x_right, int y, int value, int sx, int sy, int k) {
-  int v = value < 0 ? 0 : value;
-  for (int i = 0; i < k; i++) v /= 10;
-  if (k > 0 && v == 0) return tbx_prim_none();
-  return tbx_prim_sprite(color, x_right - 3 * sx - 4 * sx * k, y, 3, 5, TBX_BANK_FONT + 5 * (v % 10), sx, sy);
+  const uint32_t v = value < 0 ? 0u : (uint32_t)value;
+  const uint32_t p10 = k == 0 ? 1u : k == 1 ? 10u : k == 2 ? 100u : k == 3 ? 1000u : k == 4 ? 10000u : k == 5 ? 100000u
+                       : k == 6 ? 1000000u : k == 7 ? 10000000u : k == 8 ? 100000000u : 1000000000u;
+  const uint32_t q = v / p10;
+  if (k > 0 && q == 0) return tbx_prim_none();
+  return tbx_prim_sprite(color, x_right - 3 * sx - 4 * sx * k, y, 3, 5, TBX_BANK_FONT + 5 * (q % 10u), sx, sy);
 }
 #define TBX_MAX_DIGITS 10
 

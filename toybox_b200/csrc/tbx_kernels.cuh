@@ -91,6 +91,21 @@ __global__ void fill_actions_kernel(int32_t *actions, int n, uint64_t seed, uint
   if (i >= n) return;
   actions[i] = legal[tbx_action_index(seed, env0 + (uint64_t)i, t, (uint32_t)n_legal)];
 }
+/* A scripted Breakout policy for benchmarking states deep into a game (the random stream rarely breaks a brick):
+ * FIRE while waiting for a serve, otherwise move the paddle under the first ball with a slowly varying aim
+ * offset so every paddle segment gets used. */
+__global__ void breakout_tracking_actions_kernel(const uint32_t *planes, int n, int n_pad, int32_t *actions, uint64_t t) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  TbxAcc S; S.p = const_cast<uint32_t *>(planes) + env; S.stride = (size_t)n_pad;
+  int a = 0;
+  if (S.ldi(BRK_W(is_dead))) a = 1;
+  else {
+    double bx = S.ldd(BRK_W(ball)) + (double)((int)((env * 7 + t / 50) % 9) - 4), px = S.ldd(BRK_W(paddle_px));
+    a = bx > px + 1.0 ? 3 : bx < px - 1.0 ? 4 : 0;
+  }
+  actions[env] = a;
+}
 /* records (AoS, rw words each) <-> planes, for the JSON import/export of a few envs */
 __global__ void gather_kernel(const uint32_t *planes, int n_pad, const int32_t *ids, int k, int rw, uint32_t *recs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -385,6 +385,15 @@ int tbx_fill_actions(tbx_pool *p, int32_t *actions, uint64_t seed, uint64_t env0
   return TBX_OK;
 }
 
+int tbx_fill_actions_policy(tbx_pool *p, int32_t *actions, int policy, uint64_t t, void *stream) {
+  if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
+  if (policy != 1 || p->game != TBX_BREAKOUT) return set_err(TBX_EINVAL, "only policy 1 (Breakout ball tracking) is implemented");
+  CK(cudaSetDevice(p->device));
+  breakout_tracking_actions_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, actions, t);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
 int tbx_stats_read(tbx_pool *p, int64_t *out, int reset, void *stream) {
   if (!p || !out) return set_err(TBX_EINVAL, "pool/out is NULL");
   CK(cudaSetDevice(p->device));

@@ -47,7 +47,7 @@ template <> struct Traits<TBX_BREAKOUT> {
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *) { brk_new_game(S, c); }
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return brk_prim_delta(R, c, t, s, base); }
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return brk_base_id(R, c, t); }
-  static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int &b, int &e, int &mode) { brk_group(g, R, t, b, e, mode); }
+  static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int base, int &b, int &e, int &mode) { brk_group(g, R, t, base, b, e, mode); }
 };
 template <> struct Traits<TBX_SPACE_INVADERS> {
   typedef SiCfg Cfg; typedef int Table; typedef SiRec Rec;
@@ -56,7 +56,7 @@ template <> struct Traits<TBX_SPACE_INVADERS> {
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *) { si_new_game(S, c); }
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &, const Table *, int s, int) { return si_prim(R, s); }
   static __device__ __forceinline__ int base_id(const uint32_t *, const Cfg &, const Table *) { return 0; }
-  static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
+  static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
 };
 template <> struct Traits<TBX_AMIDAR> {
   typedef AmiCfg Cfg; typedef AmiTable Table; typedef AmiRec Rec;
@@ -65,7 +65,7 @@ template <> struct Traits<TBX_AMIDAR> {
   static __device__ __forceinline__ void new_game(const TbxAcc &S, const Cfg &c, const Table *t) { ami_new_game(S, c, t); }
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return ami_prim_delta(R, c, t, s, base); }
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return ami_base_id(R, c, t); }
-  static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int &b, int &e, int &mode) { ami_group(g, b, e, mode); }
+  static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { ami_group(g, b, e, mode); }
 };
 
 struct RenderArgs {
@@ -154,10 +154,19 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
   typedef Traits<GAME> T;
   constexpr int W = T::W;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  /* Barriers: painting order between two consecutive groups must be enforced across warps unless both run on
+   * warp 0 only (an in-order group, or a parallel group of at most 32 slots) -- then program order does it --
+   * or the earlier group is flagged disjoint from the next (TBX_GROUP_NOSYNC). */
+  bool have_prev = false, prev_multi = false, prev_nosync = false;
   for (int g = 0; g < T::NG; g++) {
     int gb, ge, gmode;
-    T::group(g, R, tables, gb, ge, gmode);
-    if (gb >= ge) continue; /* uniform across the CTA */
+    T::group(g, R, tables, base, gb, ge, gmode);
+    if (gb >= ge) { prev_nosync = false; continue; } /* empty group (uniform across the CTA); its neighbour's flag does not carry over */
+    const bool cur_multi = !(gmode & TBX_GROUP_SERIAL) && (ge - gb) > 32;
+    if (have_prev && (prev_multi || cur_multi) && !prev_nosync) __syncthreads();
+    have_prev = true;
+    prev_multi = cur_multi;
+    prev_nosync = (gmode & TBX_GROUP_NOSYNC) != 0;
     if (!(gmode & TBX_GROUP_SERIAL)) {
       for (int s0 = gb; s0 < ge; s0 += TBX_RENDER_THREADS) {
         const int s = s0 + tid;
@@ -222,8 +231,8 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         }
       }
     }
-    if (!(gmode & TBX_GROUP_NOSYNC)) __syncthreads();
   }
+  __syncthreads();
 }
 
 /* copy rows [r0,r1) of a base frame into the canvas (full initialisation) */
@@ -323,6 +332,10 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
       for (int r = 0; r < nr; r++) {
         const int4 rc = overflow ? make_int4(0, 0, W, H) : rects[r];
         if (rc.z <= rc.x) continue;
+        /* a small rectangle is recomputed by one warp (round robin), a large one by all warps row-interleaved */
+        const bool shared = (rc.z - rc.x) * (rc.w - rc.y) > 400;
+        if (!shared && (r % TBX_RENDER_WARPS) != wid) continue;
+        const int wsel = shared ? wid : 0, wcnt = shared ? TBX_RENDER_WARPS : 1;
         const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
         const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
         const int ncols = dx1 - dx0 + 1;
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
           float al[TX];
 #pragma unroll
           for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
-          for (int dy = dy0 + wid * rpi + sub; dy <= dy1; dy += TBX_RENDER_WARPS * rpi) {
+          for (int dy = dy0 + wsel * rpi + sub; dy <= dy1; dy += wcnt * rpi) {
             const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
             float v = 0.0f;
 #pragma unroll

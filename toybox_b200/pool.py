@@ -201,6 +201,11 @@ class BatchedToybox:
         _lib.check(self.L.tbx_fill_actions(self._h, _ptr(out), int(seed), int(env0), int(t), _stream(self.device)))
         return out
 
+    def fill_policy_actions(self, out, policy, t):
+        """Benchmark utility: scripted actions from the envs' own state (policy 1: Breakout ball tracking)."""
+        _lib.check(self.L.tbx_fill_actions_policy(self._h, _ptr(out), int(policy), int(t), _stream(self.device)))
+        return out
+
     # ------------------------------------------------------------------ scalars
     def _scalars(self):
         score = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
