@@ -236,3 +236,46 @@ def test_ctoybox_shim_and_env_surface(tbx, oracle_mod):
     obs, reward, done, info = benv.step(np.zeros(32, np.int64))
     assert tuple(obs.shape) == (32, 84, 84, 1) and int(info["lives"].min()) == 3
     benv.close()
+
+
+def test_delta_render_mixed_states_in_one_chunk(tbx, oracle_mod):
+    """Consecutive envs of a chunk share one persistent canvas: dead bricks, custom brick tables (base 0 next to
+    base 1), painted Amidar tiles and moved shields must never leak from one env's frame into the next."""
+    rng = np.random.default_rng(17)
+    n = 24
+    pool = tbx.BatchedToybox("breakout", n, seeds=100)
+    ref = oracle_mod.OracleBatch("breakout", n, seeds=100 + np.arange(n))
+    states = pool.to_state_json()
+    for i, js in enumerate(states):
+        for k in rng.choice(108, size=int(rng.integers(0, 108)), replace=False):
+            js["bricks"][int(k)]["alive"] = False
+        js["score"], js["lives"] = int(rng.integers(0, 900)), int(rng.integers(1, 6))
+        js["paddle"]["position"]["x"] = float(rng.integers(24, 216))
+        if i % 5 == 3:
+            js["bricks"][int(rng.integers(108))]["color"] = {"r": 250, "g": 250, "b": 250, "a": 255}      # custom table
+        if i % 7 == 2:
+            js["balls"].append({"position": {"x": float(rng.integers(20, 220)), "y": float(rng.integers(30, 150))},
+                                "velocity": {"x": 1.0, "y": 1.0}})
+        ref.write_state_json(i, js)
+    pool.write_state_json(states)
+    check_frames(pool, ref, n)
+    for t in range(60):
+        acts = actions_for(oracle_mod, "breakout", n, t)
+        pool.apply_ale_action(acts, auto_reset=True)
+        ref.step(acts, auto_reset=True)
+    check_frames(pool, ref, n)
+    pool.close()
+    pool = tbx.BatchedToybox("amidar", n, seeds=100)
+    ref = oracle_mod.OracleBatch("amidar", n, seeds=100 + np.arange(n))
+    states = pool.to_state_json()
+    for i, js in enumerate(states):
+        for _ in range(int(rng.integers(0, 200))):
+            ty, tx = int(rng.integers(31)), int(rng.integers(32))
+            js["board"]["tiles"][ty][tx] = ["Empty", "Unpainted", "ChaseMarker", "Painted"][int(rng.integers(4))]
+        for b in js["board"]["boxes"]:
+            b["painted"] = bool(rng.integers(2))
+        js["score"] = int(rng.integers(0, 5000))
+        ref.write_state_json(i, js)
+    pool.write_state_json(states)
+    check_frames(pool, ref, n)
+    pool.close()

@@ -17,7 +17,7 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct AreaRes { TbxAreaPlan *d_plan; uint8_t *d_base_out[2]; int dw, dh, tx, ty; };
+struct AreaRes { TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; int dw, dh, tx, ty; };
 static void drop_render_cache(struct tbx_pool *p);
 
 struct tbx_pool {
@@ -277,6 +277,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     catch (const std::exception &e) { return set_err(TBX_EINVAL, e.what()); }
     if (!tbx::build_area_plan(rs, plan)) return set_err(TBX_EINVAL, "resize: the fused kernel supports destinations up to 128x128 with at most 8 taps per axis");
     AreaRes r;
+    r.plan = plan;
     r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
@@ -302,7 +303,7 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
     configured = want;
   }
   const int H = Traits<GAME>::H;
-  dim3 grid(blocks(a.n, TBX_EPC), MODE == TBX_OBS_GRAY_AREA ? 1 : (H + a.band_rows - 1) / a.band_rows);
+  dim3 grid(blocks(a.n, TBX_EPC), ((MODE == TBX_OBS_GRAY_AREA ? a.out_h : H) + a.band_rows - 1) / a.band_rows);
   render_kernel<GAME, MODE, TX, TY><<<grid, TBX_RENDER_THREADS, smem, s>>>(a);
   CK(cudaGetLastError());
   return TBX_OK;
@@ -339,7 +340,7 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
-  a.dst = dst; a.frame_bytes = fb; a.plan = 0;
+  a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h;
   for (int b = 0; b < 2; b++) { a.base[b] = pix == 4 ? p->d_base_rgba[b] : p->d_base_gray[b]; a.base_out[b] = 0; }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
   int smem_total, tx = 1, ty = 1;
@@ -348,11 +349,23 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
     r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
     a.base_out[0] = ar->d_base_out[0]; a.base_out[1] = ar->d_base_out[1]; a.plan = ar->d_plan;
-    a.band_rows = H;
     tx = ar->tx; ty = ar->ty;
-    /* surplus (zero-weight) taps may read up to TY-1 rows past the canvas: keep them inside the allocation */
+    /* Bands of output rows: each (chunk, band) CTA keeps only the canvas rows that feed its output rows, which
+     * multiplies the number of independent CTAs per SM.  Surplus (zero-weight) taps may read up to TY-1 rows past
+     * the band's last real row: the canvas allocation covers them. */
     const int ty_inst = (tx > 5 || ty > 4) ? 8 : (ty <= 3 ? 3 : 4);
-    a.smem_rects = a.smem_canvas + align16(W * H + (ty_inst - 1) * W + 16);
+    int nb = p->game == TBX_BREAKOUT ? 4 : 2;
+    if (const char *env = getenv("TBX_AREA_BANDS")) nb = atoi(env);
+    if (nb < 1) nb = 1;
+    if (nb > out_h) nb = out_h;
+    a.band_rows = (out_h + nb - 1) / nb;
+    int canvas_rows = 0;
+    for (int d0 = 0; d0 < out_h; d0 += a.band_rows) {
+      int d1 = d0 + a.band_rows < out_h ? d0 + a.band_rows : out_h;
+      int rows = ar->plan.ys0[d1 - 1] + ty_inst - ar->plan.ys0[d0];
+      if (rows > canvas_rows) canvas_rows = rows;
+    }
+    a.smem_rects = a.smem_canvas + align16(canvas_rows * W + 16);
   } else {
     /* canvas bands of at most ~40 KB so that five CTAs stay resident per SM */
     int max_rows = (40 * 1024) / (W * pix);
@@ -361,7 +374,7 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
     a.band_rows = (H + nb - 1) / nb;
     a.smem_rects = a.smem_canvas + align16(a.band_rows * W * pix);
   }
-  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 16;
+  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 64; /* + list counts and per-env base ids */
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
   if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, smem_total, s);

@@ -77,7 +77,8 @@ struct RenderArgs {
   const uint8_t *base[2];     /* base frames 0/1: gray bytes (gray layouts) or RGBA (colour layouts) */
   const uint8_t *base_out[2]; /* INTER_AREA: their down-samples */
   const TbxAreaPlan *plan;    /* INTER_AREA */
-  int band_rows;              /* canvas rows per CTA (blockIdx.y selects the band) */
+  int band_rows;              /* per CTA (blockIdx.y selects the band): canvas rows (native layouts) / output rows (INTER_AREA) */
+  int out_h;                  /* INTER_AREA: output rows (host-side launch geometry) */
   int smem_canvas, smem_rects; /* byte offsets into dynamic shared memory */
 };
 
@@ -277,12 +278,12 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
   P *canvas = reinterpret_cast<P *>(smem + a.smem_canvas);
   int4 *rect_buf = reinterpret_cast<int4 *>(smem + a.smem_rects); /* two lists, used alternately */
   int *rect_n = reinterpret_cast<int *>(rect_buf + 2 * TBX_MAX_RECTS);
+  int *env_base = rect_n + 2; /* base frame id of each env of the chunk */
   const typename T::Cfg &cfg = *(const typename T::Cfg *)a.cfg;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
   const int ne = min(TBX_EPC, a.n - e0);
-  const int r0 = MODE == 3 ? 0 : blockIdx.y * a.band_rows, r1 = MODE == 3 ? H : min(H, r0 + a.band_rows);
 
   /* coalesced load of the chunk's state words: thread -> (word, env) with env fastest */
   for (int i = tid; i < RW * TBX_EPC; i += TBX_RENDER_THREADS) {
@@ -292,52 +293,63 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
   if (tid < 2) rect_n[tid] = 0;
   __syncthreads();
 
+  if (tid < ne) env_base[tid] = T::base_id(recs + tid * RW, cfg, tables);
+  __syncthreads();
+
   if constexpr (MODE == 3) {
-    /* the static part of every output frame of the chunk: the base frame's down-sample, global -> global */
     const TbxAreaPlan *__restrict__ plan = a.plan;
-    const int nout16 = (int)(a.frame_bytes >> 4);
-    for (int j = 0; j < ne; j++) {
-      const uint4 *src = reinterpret_cast<const uint4 *>((T::base_id(recs + j * RW, cfg, tables) ? a.base_out[1] : a.base_out[0]));
-      uint4 *dst = reinterpret_cast<uint4 *>(a.dst + (size_t)(e0 + j) * a.frame_bytes);
-      if ((a.frame_bytes & 15) == 0) {
-        for (int i = tid; i < nout16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i); /* stays in L2 until patched below */
-      } else {
-        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src);
-        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
-        for (int i = tid; i < (int)a.frame_bytes; i += TBX_RENDER_THREADS) d8[i] = s8[i];
+    const int dw = plan->dw, dh = plan->dh;
+    /* this CTA's band: output rows [d0,d1) and the canvas rows [r0,r1) that feed them (TY taps per output row) */
+    const int d0 = blockIdx.y * a.band_rows, d1 = min(dh, d0 + a.band_rows);
+    const int r0 = __ldg(&plan->ys0[d0]), r1 = min(H, (int)__ldg(&plan->ys0[d1 - 1]) + TY);
+    /* the static part of the band in every output frame of the chunk: the base frame's down-sample, global ->
+     * global (16-, 4- or 1-byte units, whatever the band's byte range allows) */
+    {
+      const int b0 = d0 * dw, b1 = d1 * dw;
+      const int align = (int)(a.frame_bytes | (size_t)b0 | (size_t)b1);
+      for (int j = 0; j < ne; j++) {
+        const uint8_t *src = env_base[j] ? a.base_out[1] : a.base_out[0];
+        uint8_t *dst = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+        if ((align & 15) == 0) {
+          for (int i = (b0 >> 4) + tid; i < (b1 >> 4); i += TBX_RENDER_THREADS) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+        } else if ((align & 3) == 0) {
+          for (int i = (b0 >> 2) + tid; i < (b1 >> 2); i += TBX_RENDER_THREADS) reinterpret_cast<uint32_t *>(dst)[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+        } else {
+          for (int i = b0 + tid; i < b1; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
+        }
       }
     }
-    const int dw = plan->dw;
     int canvas_base = -1;
     for (int j = 0; j < ne; j++) {
       const uint32_t *R = recs + j * RW;
-      const int base = T::base_id(R, cfg, tables);
+      const int base = env_base[j];
       int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
       int *n_rects = rect_n + (j & 1);
       /* bring the canvas back to the base frame (the barrier after the previous env's recompute precedes this) */
-      if (canvas_base != base) load_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), 0, H);
-      else restore_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), 0, H, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
+      if (canvas_base != base) load_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
+      else restore_canvas<1, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
       canvas_base = base;
       __syncthreads();
       if (tid == 0) rect_n[(j - 1) & 1] = 0; /* that list is reused by env j+1 */
-      paint_env<GAME, 1>(R, cfg, tables, base, canvas, 0, H, rects, n_rects);
-      /* Recompute the output pixels fed by a dirty rectangle and patch them into the destination frame (the
-       * barriers inside paint_env order these byte stores after the frame's base copy above).  Lanes own output
-       * columns (their taps stay in registers), warps own output rows; narrow rectangles pack several rows into
-       * one warp.  Straight-line TX x TY taps, surplus taps carry zero weights (x + 0*b == x for these sums). */
+      paint_env<GAME, 1>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
+      /* Recompute the band's output pixels fed by a dirty rectangle and patch them into the destination frame
+       * (the barriers above order these byte stores after the band's base copy).  Lanes own output columns (their
+       * taps stay in registers), warps own output rows; narrow rectangles pack several rows into one warp.
+       * Straight-line TX x TY taps, surplus taps carry zero weights (x + 0*b == x for these sums). */
       uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
       int nr = *n_rects;
       const bool overflow = nr > TBX_MAX_RECTS;
       if (overflow) nr = 1;
       for (int r = 0; r < nr; r++) {
-        const int4 rc = overflow ? make_int4(0, 0, W, H) : rects[r];
+        const int4 rc = overflow ? make_int4(0, r0, W, r1) : rects[r];
         if (rc.z <= rc.x) continue;
         /* a small rectangle is recomputed by one warp (round robin), a large one by all warps row-interleaved */
         const bool shared = (rc.z - rc.x) * (rc.w - rc.y) > 400;
         if (!shared && (r % TBX_RENDER_WARPS) != wid) continue;
         const int wsel = shared ? wid : 0, wcnt = shared ? TBX_RENDER_WARPS : 1;
         const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
-        const int dy0 = __ldg(&plan->ydlo[rc.y]), dy1 = __ldg(&plan->ydhi[rc.w - 1]);
+        const int dy0 = max((int)__ldg(&plan->ydlo[rc.y]), d0), dy1 = min((int)__ldg(&plan->ydhi[rc.w - 1]), d1 - 1);
+        if (dy0 > dy1) continue;
         const int ncols = dx1 - dx0 + 1;
         const int lg = ncols > 16 ? 5 : ncols > 8 ? 4 : ncols > 4 ? 3 : 2; /* columns per warp pass = 1 << lg */
         const int cpl = 1 << lg, rpi = 32 >> lg, sub = lane >> lg, c = lane & (cpl - 1);
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
 #pragma unroll
           for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
           for (int dy = dy0 + wsel * rpi + sub; dy <= dy1; dy += wcnt * rpi) {
-            const uint8_t *row = col + (size_t)__ldg(&plan->ys0[dy]) * W;
+            const uint8_t *row = col + (size_t)((int)__ldg(&plan->ys0[dy]) - r0) * W;
             float v = 0.0f;
 #pragma unroll
             for (int k = 0; k < TY; k++) {
@@ -370,10 +382,11 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
   }
 
   /* ---- native layouts: stream the band out, env after env */
+  const int r0 = blockIdx.y * a.band_rows, r1 = min(H, r0 + a.band_rows);
   int canvas_base = -1;
   for (int j = 0; j < ne; j++) {
     const uint32_t *R = recs + j * RW;
-    const int base = T::base_id(R, cfg, tables);
+    const int base = env_base[j];
     int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
     int *n_rects = rect_n + (j & 1);
     if (canvas_base != base) load_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
