@@ -28,6 +28,10 @@ TBX_HD double tbx_dsqrt(double a) { return __dsqrt_rn(a); }
 TBX_HD float tbx_fmul(float a, float b) { return __fmul_rn(a, b); }
 TBX_HD float tbx_fadd(float a, float b) { return __fadd_rn(a, b); }
 TBX_HD int tbx_f2i_rn(float v) { return __float2int_rn(v); } /* round half to even, as cvRound */
+/* the same two conversions without the quarter-rate conversion pipe: exact u8 -> f32 through the 2^23 exponent
+ * trick, and round-half-even f32 -> int for |v| < 2^22 through the 1.5 * 2^23 magic add */
+TBX_HD float tbx_u8f(uint32_t b) { return __fadd_rn(__uint_as_float(0x4B000000u | b), -8388608.0f); }
+TBX_HD int tbx_f2i_rn_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; }
 TBX_HD int tbx_ffs(uint32_t m) { return __ffs((int)m); }
 TBX_HD int tbx_popc(uint32_t m) { return __popc(m); }
 TBX_HD uint32_t tbx_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
@@ -41,6 +45,8 @@ TBX_HD double tbx_dsqrt(double a) { return sqrt(a); }
 TBX_HD float tbx_fmul(float a, float b) { return a * b; }
 TBX_HD float tbx_fadd(float a, float b) { return a + b; }
 TBX_HD int tbx_f2i_rn(float v) { return (int)lrintf(v); }
+TBX_HD float tbx_u8f(uint32_t b) { return (float)b; }
+TBX_HD int tbx_f2i_rn_small(float v) { return (int)lrintf(v); }
 TBX_HD int tbx_ffs(uint32_t m) { return __builtin_ffs((int)m); }
 TBX_HD int tbx_popc(uint32_t m) { return __builtin_popcount(m); }
 TBX_HD uint32_t tbx_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -244,9 +250,19 @@ TBX_HD bool tbx_prim_covers(const TbxPrim &p, const uint32_t *bank, const uint32
  * mirrors the HUD digit layout of the draw lists (3x5 font, 1 column gap) */
 TBX_HD TbxPrim tbx_prim_digit(uint32_t color, int x_right, int y, int value, int sx, int sy, int k) {
   const uint32_t v = value < 0 ? 0u : (uint32_t)value;
-  const uint32_t p10 = k == 0 ? 1u : k == 1 ? 10u : k == 2 ? 100u : k == 3 ? 1000u : k == 4 ? 10000u : k == 5 ? 100000u
-                       : k == 6 ? 1000000u : k == 7 ? 10000000u : k == 8 ? 100000000u : 1000000000u;
-  const uint32_t q = v / p10;
+  uint32_t q; /* v / 10^k with compile-time divisors (multiply-shift, no division unit) */
+  switch (k) {
+    case 0: q = v; break;
+    case 1: q = v / 10u; break;
+    case 2: q = v / 100u; break;
+    case 3: q = v / 1000u; break;
+    case 4: q = v / 10000u; break;
+    case 5: q = v / 100000u; break;
+    case 6: q = v / 1000000u; break;
+    case 7: q = v / 10000000u; break;
+    case 8: q = v / 100000000u; break;
+    default: q = v / 1000000000u; break;
+  }
   if (k > 0 && q == 0) return tbx_prim_none();
   return tbx_prim_sprite(color, x_right - 3 * sx - 4 * sx * k, y, 3, 5, TBX_BANK_FONT + 5 * (q % 10u), sx, sy);
 }

@@ -38,6 +38,8 @@ namespace tbxk {
 #define TBX_MAX_RECTS 96
 
 __device__ const uint32_t d_bank[TBX_BANK_WORDS] = TBX_BANK_INIT;
+/* ceil(65536 / s) for the sprite scale factors s = 1..15 */
+__device__ const uint32_t d_inv16[16] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370};
 
 template <int GAME> struct Traits;
 template <> struct Traits<TBX_BREAKOUT> {
@@ -118,23 +120,28 @@ template <int PIX, int W>
 __device__ __forceinline__ void paint_coop(typename PixT<PIX>::T *canvas, int r0, const Clip &c, int qx, int qy, uint32_t val, uint32_t q3,
                                            const uint32_t *rec, int lane) {
   typedef typename PixT<PIX>::T P;
-  const int nw = c.x1 - c.x0, cnt = nw * (c.y1 - c.y0);
-  const float inv_nw = 1.0f / (float)nw;
+  /* lanes tile the rectangle as (32 >> lg) rows x (1 << lg) columns per pass: no divisions, no int<->float
+   * conversions (those run on the quarter-rate XU pipe, which an earlier version of this kernel saturated) */
+  const int nw = c.x1 - c.x0, nh = c.y1 - c.y0;
+  const int lg = nw > 16 ? 5 : nw > 8 ? 4 : nw > 4 ? 3 : nw > 2 ? 2 : nw > 1 ? 1 : 0;
+  const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
   const int bw = (q3 >> 16) & 255;
   if (bw == 0) {
-    for (int i = lane; i < cnt; i += 32) {
-      int yy = (int)(((float)i + 0.5f) * inv_nw), xx = i - yy * nw;
-      canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xx] = (P)val;
-    }
+    for (int xb = cx; xb < nw; xb += cpl)
+      for (int yy = sub; yy < nh; yy += rpp) canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xb] = (P)val;
   } else {
     const uint32_t off = q3 & 0xffffu;
     const uint32_t *rows = (off & TBX_PRIM_STATE) ? rec + (off & 0x7fffu) : d_bank + off;
     const int sx = (q3 >> 24) & 15, sy = q3 >> 28;
-    const float inv_sx = 1.0f / (float)sx, inv_sy = 1.0f / (float)sy;
-    for (int i = lane; i < cnt; i += 32) {
-      int yy = (int)(((float)i + 0.5f) * inv_nw), xx = i - yy * nw;
-      int sy_i = (int)(((float)(c.y0 + yy - qy) + 0.5f) * inv_sy), sx_i = (int)(((float)(c.x0 + xx - qx) + 0.5f) * inv_sx);
-      if ((rows[sy_i] >> (bw - 1 - sx_i)) & 1u) canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xx] = (P)val;
+    const uint32_t ix = d_inv16[sx], iy = d_inv16[sy]; /* v / s == (v * ceil(65536 / s)) >> 16 for v < 4096 */
+    for (int xb = cx; xb < nw; xb += cpl) {
+      const int px = c.x0 + xb - qx;
+      const int sx_i = sx == 1 ? px : (int)(((uint32_t)px * ix) >> 16);
+      for (int yy = sub; yy < nh; yy += rpp) {
+        const int py = c.y0 + yy - qy;
+        const int sy_i = sy == 1 ? py : (int)(((uint32_t)py * iy) >> 16);
+        if ((rows[sy_i] >> (bw - 1 - sx_i)) & 1u) canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xb] = (P)val;
+      }
     }
   }
 }
@@ -195,10 +202,22 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
             paint_coop<PIX, W>(canvas, r0, qc, q.x, q.y, qv, q3, R, lane);
           }
         }
-        /* this warp pass's bounding box (hardware integer warp reductions) */
+        /* dirty area of this warp pass (hardware integer warp reductions): its bounding box when the primitives
+         * fill it densely (bricks, tiles), else one rectangle per primitive (sprites spread over a formation) */
         const int bx0 = __reduce_min_sync(0xffffffffu, ok ? c.x0 : 32767), by0 = __reduce_min_sync(0xffffffffu, ok ? c.y0 : 32767);
         const int bx1 = __reduce_max_sync(0xffffffffu, ok ? c.x1 : -1), by1 = __reduce_max_sync(0xffffffffu, ok ? c.y1 : -1);
-        if (lane == 0) push_rect(rects, n_rects, make_int4(bx0, by0, bx1, by1));
+        const int covered = __reduce_add_sync(0xffffffffu, ok ? (c.x1 - c.x0) * (c.y1 - c.y0) : 0);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int room = __shfl_sync(0xffffffffu, TBX_MAX_RECTS - 40 - *(volatile int *)n_rects, 0); /* keep room for the later groups */
+        if ((bx1 - bx0) * (by1 - by0) <= 2 * covered || __popc(m) > room) {
+          if (lane == 0) push_rect(rects, n_rects, make_int4(bx0, by0, bx1, by1));
+        } else {
+          int slot0 = 0;
+          if (lane == 0) slot0 = atomicAdd(n_rects, __popc(m));
+          slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+          const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
+          if (ok && slot < TBX_MAX_RECTS) rects[slot] = make_int4(c.x0, c.y0, c.x1, c.y1);
+        }
       }
     } else if (wid == 0) {
       /* in order: lane l builds primitive gb + 32*batch + l, then the warp paints them one at a time */
@@ -254,13 +273,14 @@ __device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, co
     const int4 rc = rects[i];
     if (rc.z <= rc.x) continue;
     const int b0 = (rc.x * PIX) & ~15, b1 = (rc.z * PIX + 15) & ~15, nch = (b1 - b0) >> 4;
-    const int cnt = nch * (rc.w - rc.y);
-    const float inv = 1.0f / (float)nch;
-    for (int k = lane; k < cnt; k += 32) {
-      const int yy = (int)(((float)k + 0.5f) * inv), ch = k - yy * nch;
-      const size_t off = (size_t)(rc.y + yy) * W * PIX + b0 + 16 * ch;
-      *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(canvas) + off - (size_t)r0 * W * PIX) = __ldg(reinterpret_cast<const uint4 *>(base + off));
-    }
+    const int nh = rc.w - rc.y;
+    const int lg = nch > 16 ? 5 : nch > 8 ? 4 : nch > 4 ? 3 : nch > 2 ? 2 : nch > 1 ? 1 : 0;
+    const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
+    for (int ch = cx; ch < nch; ch += cpl)
+      for (int yy = sub; yy < nh; yy += rpp) {
+        const size_t off = (size_t)(rc.y + yy) * W * PIX + b0 + 16 * ch;
+        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(canvas) + off - (size_t)r0 * W * PIX) = __ldg(reinterpret_cast<const uint4 *>(base + off));
+      }
   }
 }
 
@@ -365,13 +385,13 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
             float v = 0.0f;
 #pragma unroll
             for (int k = 0; k < TY; k++) {
-              float h = tbx_fmul((float)row[k * W], al[0]);
+              float h = tbx_fmul(tbx_u8f(row[k * W]), al[0]);
 #pragma unroll
-              for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul((float)row[k * W + t], al[t]));
+              for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(row[k * W + t]), al[t]));
               const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
               v = k == 0 ? bh : tbx_fadd(v, bh);
             }
-            const int iv = tbx_f2i_rn(v);
+            const int iv = tbx_f2i_rn_small(v);
             if (colok) out[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
           }
         }
