@@ -304,7 +304,10 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
   }
   const int H = Traits<GAME>::H;
   dim3 grid(blocks(a.n, TBX_EPC), ((MODE == TBX_OBS_GRAY_AREA ? a.out_h : H) + a.band_rows - 1) / a.band_rows);
-  render_kernel<GAME, MODE, TX, TY><<<grid, TBX_RENDER_THREADS, smem, s>>>(a);
+  int threads = MODE == TBX_OBS_GRAY_AREA ? 128 : 256;
+  if (const char *env = getenv("TBX_RENDER_THREADS")) threads = atoi(env); /* tuning: 32, 64, 128 or 256 */
+  if (threads != 32 && threads != 64 && threads != 128 && threads != 256) threads = 128;
+  render_kernel<GAME, MODE, TX, TY><<<grid, threads, smem, s>>>(a);
   CK(cudaGetLastError());
   return TBX_OK;
 }
@@ -354,7 +357,7 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
      * multiplies the number of independent CTAs per SM.  Surplus (zero-weight) taps may read up to TY-1 rows past
      * the band's last real row: the canvas allocation covers them. */
     const int ty_inst = (tx > 5 || ty > 4) ? 8 : (ty <= 3 ? 3 : 4);
-    int nb = p->game == TBX_BREAKOUT ? 4 : 2;
+    int nb = p->game == TBX_AMIDAR ? 1 : 2;
     if (const char *env = getenv("TBX_AREA_BANDS")) nb = atoi(env);
     if (nb < 1) nb = 1;
     if (nb > out_h) nb = out_h;

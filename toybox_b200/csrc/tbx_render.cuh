@@ -27,13 +27,13 @@
 
 namespace tbxk {
 
-#ifndef TBX_RENDER_THREADS
-#define TBX_RENDER_THREADS 256
-#endif
-#ifndef TBX_RENDER_MIN_CTAS
+/* The kernel is compiled for up to 256 threads and 64 registers per thread (4 x 256 or 8 x 128 threads per SM);
+ * the launch picks the CTA size per layout: the INTER_AREA layout does little work per env and runs best as many
+ * small CTAs, the native layouts stream whole bands and like wide ones.  The CTA size is a power of two. */
+#define TBX_RENDER_MAX_THREADS 256
 #define TBX_RENDER_MIN_CTAS 4
-#endif
-#define TBX_RENDER_WARPS (TBX_RENDER_THREADS / 32)
+#define TBX_NT ((int)blockDim.x)
+#define TBX_NW ((int)(blockDim.x >> 5))
 #define TBX_EPC 8
 #define TBX_MAX_RECTS 96
 
@@ -176,7 +176,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
     prev_multi = cur_multi;
     prev_nosync = (gmode & TBX_GROUP_NOSYNC) != 0;
     if (!(gmode & TBX_GROUP_SERIAL)) {
-      for (int s0 = gb; s0 < ge; s0 += TBX_RENDER_THREADS) {
+      for (int s0 = gb; s0 < ge; s0 += TBX_NT) {
         const int s = s0 + tid;
         TbxPrim p = tbx_prim_none();
         if (s < ge) p = T::prim(R, cfg, tables, s, base);
@@ -262,14 +262,14 @@ __device__ __forceinline__ void load_canvas(typename PixT<PIX>::T *canvas, const
   uint4 *dst = reinterpret_cast<uint4 *>(canvas);
   const int n16 = (r1 - r0) * W * PIX / 16;
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n16; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < n16; i += TBX_NT) dst[i] = __ldg(src + i);
 }
 /* undo one env's painting: re-copy the dirty rectangles (whole 16-byte chunks) from the base frame */
 template <int PIX, int W>
 __device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, const uint8_t *base, int r0, int r1, const int4 *rects, int n) {
   if (n > TBX_MAX_RECTS) { load_canvas<PIX, W>(canvas, base, r0, r1); return; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = wid; i < n; i += TBX_RENDER_WARPS) {
+  for (int i = wid; i < n; i += TBX_NW) {
     const int4 rc = rects[i];
     if (rc.z <= rc.x) continue;
     const int b0 = (rc.x * PIX) & ~15, b1 = (rc.z * PIX + 15) & ~15, nch = (b1 - b0) >> 4;
@@ -287,7 +287,7 @@ __device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, co
 /* MODE: TBX_OBS_RGBA (0), TBX_OBS_RGB (1), TBX_OBS_GRAY (2), TBX_OBS_GRAY_AREA (3).
  * TX, TY: taps per output column / row of the INTER_AREA plan (>= plan.tx, plan.ty; surplus taps have zero weight). */
 template <int GAME, int MODE, int TX, int TY>
-__global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
   constexpr int PIX = (MODE == 0 || MODE == 1) ? 4 : 1;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
   const int ne = min(TBX_EPC, a.n - e0);
 
   /* coalesced load of the chunk's state words: thread -> (word, env) with env fastest */
-  for (int i = tid; i < RW * TBX_EPC; i += TBX_RENDER_THREADS) {
+  for (int i = tid; i < RW * TBX_EPC; i += TBX_NT) {
     int w = i / TBX_EPC, j = i - w * TBX_EPC;
     if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
   }
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
         const uint8_t *src = env_base[j] ? a.base_out[1] : a.base_out[0];
         uint8_t *dst = a.dst + (size_t)(e0 + j) * a.frame_bytes;
         if ((align & 15) == 0) {
-          for (int i = (b0 >> 4) + tid; i < (b1 >> 4); i += TBX_RENDER_THREADS) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+          for (int i = (b0 >> 4) + tid; i < (b1 >> 4); i += TBX_NT) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
         } else if ((align & 3) == 0) {
-          for (int i = (b0 >> 2) + tid; i < (b1 >> 2); i += TBX_RENDER_THREADS) reinterpret_cast<uint32_t *>(dst)[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+          for (int i = (b0 >> 2) + tid; i < (b1 >> 2); i += TBX_NT) reinterpret_cast<uint32_t *>(dst)[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
         } else {
-          for (int i = b0 + tid; i < b1; i += TBX_RENDER_THREADS) dst[i] = __ldg(src + i);
+          for (int i = b0 + tid; i < b1; i += TBX_NT) dst[i] = __ldg(src + i);
         }
       }
     }
@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
         if (rc.z <= rc.x) continue;
         /* a small rectangle is recomputed by one warp (round robin), a large one by all warps row-interleaved */
         const bool shared = (rc.z - rc.x) * (rc.w - rc.y) > 400;
-        if (!shared && (r % TBX_RENDER_WARPS) != wid) continue;
-        const int wsel = shared ? wid : 0, wcnt = shared ? TBX_RENDER_WARPS : 1;
+        if (!shared && (r & (TBX_NW - 1)) != wid) continue;
+        const int wsel = shared ? wid : 0, wcnt = shared ? TBX_NW : 1;
         const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
         const int dy0 = max((int)__ldg(&plan->ydlo[rc.y]), d0), dy1 = min((int)__ldg(&plan->ydhi[rc.w - 1]), d1 - 1);
         if (dy0 > dy1) continue;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
       const int groups = (r1 - r0) * W / 16;
       const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
       uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * 3);
-      for (int g = tid; g < groups; g += TBX_RENDER_THREADS) {
+      for (int g = tid; g < groups; g += TBX_NT) {
         uint32_t p[16];
 #pragma unroll
         for (int k = 0; k < 4; k++) { uint4 v = src[g * 4 + k]; p[4 * k] = v.x; p[4 * k + 1] = v.y; p[4 * k + 2] = v.z; p[4 * k + 3] = v.w; }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(TBX_RENDER_THREADS, TBX_RENDER_MIN_CTAS) rende
       const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
       uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * PIX);
 #pragma unroll 4
-      for (int i = tid; i < n16; i += TBX_RENDER_THREADS) __stcs(dst + i, src[i]);
+      for (int i = tid; i < n16; i += TBX_NT) __stcs(dst + i, src[i]);
     }
     __syncthreads();
   }
