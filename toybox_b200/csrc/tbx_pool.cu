@@ -34,7 +34,7 @@ struct tbx_pool {
   int *d_bad;
   int32_t *d_legal;
   /* render resources of the current config: static frame (gray, RGBA) and per output size the INTER_AREA plan */
-  uint8_t *d_base_gray[2], *d_base_rgba[2];
+  uint8_t *d_base_gray[2], *d_base_rgba[2], *d_base_rgb[2];
   std::vector<uint32_t> h_base_rgba[2];
   std::vector<uint8_t> h_base_gray[2];
   std::map<std::pair<int, int>, struct AreaRes> area;
@@ -124,7 +124,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   tbx_pool *p = new (std::nothrow) tbx_pool();
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
-  p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
+  p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = p->d_base_rgb[0] = p->d_base_rgb[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
   p->hs = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
@@ -246,7 +246,7 @@ int tbx_check(tbx_pool *p, void *stream) {
 
 /* ---- render */
 static void drop_render_cache(tbx_pool *p) {
-  for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); p->d_base_gray[b] = p->d_base_rgba[b] = 0; }
+  for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); cudaFree(p->d_base_rgb[b]); p->d_base_gray[b] = p->d_base_rgba[b] = p->d_base_rgb[b] = 0; }
   for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); }
   p->area.clear();
 }
@@ -264,6 +264,10 @@ static int ensure_base(tbx_pool *p) {
     CK(cudaMalloc(&p->d_base_rgba[b], (size_t)npix * 4));
     CK(cudaMemcpy(p->d_base_gray[b], p->h_base_gray[b].data(), npix, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_base_rgba[b], p->h_base_rgba[b].data(), (size_t)npix * 4, cudaMemcpyHostToDevice));
+    std::vector<uint8_t> rgb((size_t)npix * 3);
+    for (int i = 0; i < npix; i++) { uint32_t c = p->h_base_rgba[b][i]; rgb[3 * i] = c & 255; rgb[3 * i + 1] = (c >> 8) & 255; rgb[3 * i + 2] = (c >> 16) & 255; }
+    CK(cudaMalloc(&p->d_base_rgb[b], rgb.size()));
+    CK(cudaMemcpy(p->d_base_rgb[b], rgb.data(), rgb.size(), cudaMemcpyHostToDevice));
   }
   return TBX_OK;
 }
@@ -344,7 +348,10 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h;
-  for (int b = 0; b < 2; b++) { a.base[b] = pix == 4 ? p->d_base_rgba[b] : p->d_base_gray[b]; a.base_out[b] = 0; }
+  for (int b = 0; b < 2; b++) {
+    a.base[b] = pix == 4 ? p->d_base_rgba[b] : p->d_base_gray[b];
+    a.base_out[b] = mode == TBX_OBS_RGB ? p->d_base_rgb[b] : a.base[b]; /* INTER_AREA: set below */
+  }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
   int smem_total, tx = 1, ty = 1;
   if (mode == TBX_OBS_GRAY_AREA) {

@@ -77,7 +77,7 @@ struct RenderArgs {
   uint8_t *dst;
   size_t frame_bytes;
   const uint8_t *base[2];     /* base frames 0/1: gray bytes (gray layouts) or RGBA (colour layouts) */
-  const uint8_t *base_out[2]; /* INTER_AREA: their down-samples */
+  const uint8_t *base_out[2]; /* the base frames in the OUTPUT format: INTER_AREA down-samples / gray / RGBA / packed RGB */
   const TbxAreaPlan *plan;    /* INTER_AREA */
   int band_rows;              /* per CTA (blockIdx.y selects the band): canvas rows (native layouts) / output rows (INTER_AREA) */
   int out_h;                  /* INTER_AREA: output rows (host-side launch geometry) */
@@ -401,7 +401,11 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     return;
   }
 
-  /* ---- native layouts: stream the band out, env after env */
+  /* ---- native layouts.  Outside the dirty rectangles an env's frame IS the base frame, so the band is copied
+   * global -> global from the base frame in its output format (a straight, fully coalesced 16-byte copy that runs
+   * at memory speed, independent of the painting) and only the dirty rectangles are patched in from the canvas:
+   * 4-byte columns for gray, pixels for RGBA, groups of 4 pixels -> 12 bytes for RGB. */
+  constexpr int OPIX = MODE == 0 ? 4 : MODE == 1 ? 3 : 1; /* output bytes per pixel */
   const int r0 = blockIdx.y * a.band_rows, r1 = min(H, r0 + a.band_rows);
   int canvas_base = -1;
   for (int j = 0; j < ne; j++) {
@@ -409,41 +413,62 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     const int base = env_base[j];
     int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
     int *n_rects = rect_n + (j & 1);
+    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>((base ? a.base_out[1] : a.base_out[0]) + (size_t)r0 * W * OPIX);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * OPIX);
+      const int n16 = (r1 - r0) * W * OPIX / 16;
+#pragma unroll 4
+      for (int i = tid; i < n16; i += TBX_NT) dst[i] = __ldg(src + i);
+    }
     if (canvas_base != base) load_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
     else restore_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
     canvas_base = base;
     __syncthreads();
     if (tid == 0) rect_n[(j - 1) & 1] = 0;
     paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
-    if (MODE == 1) {
-      /* 16 pixels (64 B of RGBA) -> 48 B of RGB, three 16-byte stores per thread */
-      const int groups = (r1 - r0) * W / 16;
-      const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
-      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * 3);
-      for (int g = tid; g < groups; g += TBX_NT) {
-        uint32_t p[16];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { uint4 v = src[g * 4 + k]; p[4 * k] = v.x; p[4 * k + 1] = v.y; p[4 * k + 2] = v.z; p[4 * k + 3] = v.w; }
-        uint32_t o[12];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { /* 4 pixels -> 3 words (byte permutes) */
-          o[3 * k] = __byte_perm(p[4 * k], p[4 * k + 1], 0x4210);
-          o[3 * k + 1] = __byte_perm(p[4 * k + 1], p[4 * k + 2], 0x5421);
-          o[3 * k + 2] = __byte_perm(p[4 * k + 2], p[4 * k + 3], 0x6542);
-        }
-        __stcs(dst + g * 3, make_uint4(o[0], o[1], o[2], o[3]));
-        __stcs(dst + g * 3 + 1, make_uint4(o[4], o[5], o[6], o[7]));
-        __stcs(dst + g * 3 + 2, make_uint4(o[8], o[9], o[10], o[11]));
+    /* patch the dirty rectangles (the barriers above order these stores after the band's base copy) */
+    int nr = *n_rects;
+    const bool overflow = nr > TBX_MAX_RECTS;
+    if (overflow) nr = 1;
+    for (int r = wid; r < nr; r += TBX_NW) {
+      const int4 rc = overflow ? make_int4(0, r0, W, r1) : rects[r];
+      if (rc.z <= rc.x) continue;
+      const int nh = rc.w - rc.y;
+      if (MODE == 2) { /* gray: aligned 4-byte columns */
+        const int w0 = rc.x >> 2, nwd = ((rc.z + 3) >> 2) - w0;
+        const int lg = nwd > 16 ? 5 : nwd > 8 ? 4 : nwd > 4 ? 3 : nwd > 2 ? 2 : nwd > 1 ? 1 : 0;
+        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
+        for (int xw = cx; xw < nwd; xw += cpl)
+          for (int yy = sub; yy < nh; yy += rpp) {
+            const int y = rc.y + yy;
+            reinterpret_cast<uint32_t *>(out + (size_t)y * W)[w0 + xw] = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(canvas) + (size_t)(y - r0) * W)[w0 + xw];
+          }
+      } else if (MODE == 0) { /* RGBA: pixels */
+        const int nwd = rc.z - rc.x;
+        const int lg = nwd > 16 ? 5 : nwd > 8 ? 4 : nwd > 4 ? 3 : nwd > 2 ? 2 : nwd > 1 ? 1 : 0;
+        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
+        for (int xw = cx; xw < nwd; xw += cpl)
+          for (int yy = sub; yy < nh; yy += rpp) {
+            const int y = rc.y + yy;
+            reinterpret_cast<uint32_t *>(out + (size_t)y * W * 4)[rc.x + xw] = reinterpret_cast<const uint32_t *>(canvas)[(size_t)(y - r0) * W + rc.x + xw];
+          }
+      } else { /* RGB: groups of 4 pixels (16 B of RGBA) -> 12 B */
+        const int g0 = rc.x >> 2, ng = ((rc.z + 3) >> 2) - g0;
+        const int lg = ng > 16 ? 5 : ng > 8 ? 4 : ng > 4 ? 3 : ng > 2 ? 2 : ng > 1 ? 1 : 0;
+        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
+        for (int xg = cx; xg < ng; xg += cpl)
+          for (int yy = sub; yy < nh; yy += rpp) {
+            const int y = rc.y + yy;
+            const uint4 v = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(canvas) + (size_t)(y - r0) * W)[g0 + xg];
+            uint32_t *d = reinterpret_cast<uint32_t *>(out + (size_t)y * W * 3) + 3 * (g0 + xg);
+            d[0] = __byte_perm(v.x, v.y, 0x4210);
+            d[1] = __byte_perm(v.y, v.z, 0x5421);
+            d[2] = __byte_perm(v.z, v.w, 0x6542);
+          }
       }
-    } else {
-      const int n16 = (r1 - r0) * W * PIX / 16;
-      const uint4 *src = reinterpret_cast<const uint4 *>(canvas);
-      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * PIX);
-#pragma unroll 4
-      for (int i = tid; i < n16; i += TBX_NT) __stcs(dst + i, src[i]);
     }
-    __syncthreads();
+    __syncthreads(); /* the canvas is restored next */
   }
 }
 
