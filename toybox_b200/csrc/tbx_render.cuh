@@ -401,12 +401,24 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     return;
   }
 
-  /* ---- native layouts.  Outside the dirty rectangles an env's frame IS the base frame, so the band is copied
-   * global -> global from the base frame in its output format (a straight, fully coalesced 16-byte copy that runs
-   * at memory speed, independent of the painting) and only the dirty rectangles are patched in from the canvas:
-   * 4-byte columns for gray, pixels for RGBA, groups of 4 pixels -> 12 bytes for RGB. */
+  /* ---- native layouts.
+   * gray / RGBA: the painted canvas band IS the output band: it leaves through the TMA engine, one bulk
+   * shared -> global copy per env (cp.async.bulk), no per-thread load/store instructions.
+   * RGB (3 bytes per pixel, the canvas holds 4): outside the dirty rectangles the frame is the base frame, so the
+   * band is first copied global -> global from the PACKED base frame for the whole chunk (a straight, coalesced
+   * 16-byte copy with the chunk's 8 bands in flight), then only the dirty rectangles are packed from the canvas
+   * (groups of 4 pixels -> 12 bytes) and patched in. */
   constexpr int OPIX = MODE == 0 ? 4 : MODE == 1 ? 3 : 1; /* output bytes per pixel */
   const int r0 = blockIdx.y * a.band_rows, r1 = min(H, r0 + a.band_rows);
+  if (MODE == 1) {
+    const int n16 = (r1 - r0) * W * OPIX / 16;
+    for (int j = 0; j < ne; j++) {
+      const uint4 *src = reinterpret_cast<const uint4 *>((env_base[j] ? a.base_out[1] : a.base_out[0]) + (size_t)r0 * W * OPIX);
+      uint4 *dst = reinterpret_cast<uint4 *>(a.dst + (size_t)(e0 + j) * a.frame_bytes + (size_t)r0 * W * OPIX);
+#pragma unroll 4
+      for (int i = tid; i < n16; i += TBX_NT) dst[i] = __ldg(src + i);
+    }
+  }
   int canvas_base = -1;
   for (int j = 0; j < ne; j++) {
     const uint32_t *R = recs + j * RW;
@@ -414,46 +426,34 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
     int *n_rects = rect_n + (j & 1);
     uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>((base ? a.base_out[1] : a.base_out[0]) + (size_t)r0 * W * OPIX);
-      uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r0 * W * OPIX);
-      const int n16 = (r1 - r0) * W * OPIX / 16;
-#pragma unroll 4
-      for (int i = tid; i < n16; i += TBX_NT) dst[i] = __ldg(src + i);
-    }
     if (canvas_base != base) load_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
     else restore_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
     canvas_base = base;
     __syncthreads();
     if (tid == 0) rect_n[(j - 1) & 1] = 0;
     paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
-    /* patch the dirty rectangles (the barriers above order these stores after the band's base copy) */
-    int nr = *n_rects;
-    const bool overflow = nr > TBX_MAX_RECTS;
-    if (overflow) nr = 1;
-    for (int r = wid; r < nr; r += TBX_NW) {
-      const int4 rc = overflow ? make_int4(0, r0, W, r1) : rects[r];
-      if (rc.z <= rc.x) continue;
-      const int nh = rc.w - rc.y;
-      if (MODE == 2) { /* gray: aligned 4-byte columns */
-        const int w0 = rc.x >> 2, nwd = ((rc.z + 3) >> 2) - w0;
-        const int lg = nwd > 16 ? 5 : nwd > 8 ? 4 : nwd > 4 ? 3 : nwd > 2 ? 2 : nwd > 1 ? 1 : 0;
-        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
-        for (int xw = cx; xw < nwd; xw += cpl)
-          for (int yy = sub; yy < nh; yy += rpp) {
-            const int y = rc.y + yy;
-            reinterpret_cast<uint32_t *>(out + (size_t)y * W)[w0 + xw] = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(canvas) + (size_t)(y - r0) * W)[w0 + xw];
-          }
-      } else if (MODE == 0) { /* RGBA: pixels */
-        const int nwd = rc.z - rc.x;
-        const int lg = nwd > 16 ? 5 : nwd > 8 ? 4 : nwd > 4 ? 3 : nwd > 2 ? 2 : nwd > 1 ? 1 : 0;
-        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
-        for (int xw = cx; xw < nwd; xw += cpl)
-          for (int yy = sub; yy < nh; yy += rpp) {
-            const int y = rc.y + yy;
-            reinterpret_cast<uint32_t *>(out + (size_t)y * W * 4)[rc.x + xw] = reinterpret_cast<const uint32_t *>(canvas)[(size_t)(y - r0) * W + rc.x + xw];
-          }
-      } else { /* RGB: groups of 4 pixels (16 B of RGBA) -> 12 B */
+    if (MODE != 1) {
+      /* one bulk shared -> global copy of the painted band through the TMA engine.  Every thread first makes its
+       * canvas writes visible to the async proxy; the canvas may be touched again once the engine has read it. */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(canvas);
+        const uint32_t nbytes = (uint32_t)((r1 - r0) * W * OPIX);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)r0 * W * OPIX), "r"(saddr), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {
+      /* patch the dirty rectangles (the barriers above order these stores after the band's base copy):
+       * groups of 4 pixels (16 B of RGBA in the canvas) -> 12 B */
+      int nr = *n_rects;
+      const bool overflow = nr > TBX_MAX_RECTS;
+      if (overflow) nr = 1;
+      for (int r = wid; r < nr; r += TBX_NW) {
+        const int4 rc = overflow ? make_int4(0, r0, W, r1) : rects[r];
+        if (rc.z <= rc.x) continue;
+        const int nh = rc.w - rc.y;
         const int g0 = rc.x >> 2, ng = ((rc.z + 3) >> 2) - g0;
         const int lg = ng > 16 ? 5 : ng > 8 ? 4 : ng > 4 ? 3 : ng > 2 ? 2 : ng > 1 ? 1 : 0;
         const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     }
     __syncthreads(); /* the canvas is restored next */
   }
+  if (MODE != 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* all bands have left */
 }
 
 } /* namespace tbxk */
