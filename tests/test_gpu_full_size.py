@@ -49,8 +49,9 @@ def sample_check(tbx, oracle_mod, game, n, obs, steps, sample, mutate=None, ever
     out2 = torch.empty_like(out)
     pool.render(out=out2)
     assert torch.equal(out, out2)
-    per_env = out.reshape(n, -1).sum(dim=1, dtype=torch.int64)
     del out2
+    flat = out.reshape(n, -1)
+    per_env = torch.cat([flat[i:i + 4096].sum(dim=1, dtype=torch.int64) for i in range(0, n, 4096)])
     assert int(per_env.sum()) == int(per_env.flip(0).cumsum(0)[-1])
     stats = pool.episode_stats()
     assert stats[0] >= 0 and stats[2] >= stats[0]
