@@ -344,13 +344,13 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   int r = ensure_base(p);
   if (r) return r;
   const int W = p->info->width, H = p->info->height;
-  const int pix = (mode == TBX_OBS_RGBA || mode == TBX_OBS_RGB) ? 4 : 1;
+  const int pix = mode == TBX_OBS_RGBA ? 4 : mode == TBX_OBS_RGB ? 3 : 1; /* canvas bytes per pixel */
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h;
   for (int b = 0; b < 2; b++) {
-    a.base[b] = pix == 4 ? p->d_base_rgba[b] : p->d_base_gray[b];
-    a.base_out[b] = mode == TBX_OBS_RGB ? p->d_base_rgb[b] : a.base[b]; /* INTER_AREA: set below */
+    a.base[b] = pix == 4 ? p->d_base_rgba[b] : pix == 3 ? p->d_base_rgb[b] : p->d_base_gray[b];
+    a.base_out[b] = 0; /* INTER_AREA: set below */
   }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
   int smem_total, tx = 1, ty = 1;

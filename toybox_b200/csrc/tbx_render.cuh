@@ -76,17 +76,21 @@ struct RenderArgs {
   const void *cfg, *tables;
   uint8_t *dst;
   size_t frame_bytes;
-  const uint8_t *base[2];     /* base frames 0/1: gray bytes (gray layouts) or RGBA (colour layouts) */
-  const uint8_t *base_out[2]; /* the base frames in the OUTPUT format: INTER_AREA down-samples / gray / RGBA / packed RGB */
+  const uint8_t *base[2];     /* base frames 0/1 in the canvas format: gray bytes, packed RGB or RGBA */
+  const uint8_t *base_out[2]; /* INTER_AREA: their down-samples */
   const TbxAreaPlan *plan;    /* INTER_AREA */
   int band_rows;              /* per CTA (blockIdx.y selects the band): canvas rows (native layouts) / output rows (INTER_AREA) */
   int out_h;                  /* INTER_AREA: output rows (host-side launch geometry) */
   int smem_canvas, smem_rects; /* byte offsets into dynamic shared memory */
 };
 
-template <int PIX> struct PixT;
-template <> struct PixT<1> { typedef uint8_t T; };
-template <> struct PixT<4> { typedef uint32_t T; };
+/* The canvas is a byte array with PIX bytes per pixel: 1 = gray, 3 = packed RGB, 4 = RGBA.  `val` is the colour
+ * as RGBA (r | g<<8 | b<<16 | a<<24) for PIX 3 and 4, the gray byte for PIX 1. */
+template <int PIX> __device__ __forceinline__ void put_pixel(uint8_t *canvas, size_t pix, uint32_t val) {
+  if (PIX == 1) canvas[pix] = (uint8_t)val;
+  else if (PIX == 4) reinterpret_cast<uint32_t *>(canvas)[pix] = val;
+  else { uint8_t *p = canvas + 3 * pix; p[0] = (uint8_t)val; p[1] = (uint8_t)(val >> 8); p[2] = (uint8_t)(val >> 16); }
+}
 
 struct Clip { int x0, y0, x1, y1; };
 template <int W> __device__ __forceinline__ bool clip_prim(const TbxPrim &p, int r0, int r1, Clip &c) {
@@ -95,40 +99,45 @@ template <int W> __device__ __forceinline__ bool clip_prim(const TbxPrim &p, int
   return p.h > 0 && c.x0 < c.x1 && c.y0 < c.y1;
 }
 
-/* one thread fills a small solid rectangle: aligned 32-bit span stores for the 1-byte canvas */
+/* one thread fills a small solid rectangle: 32-bit stores over the aligned middle of each row (4 gray pixels per
+ * word; 4 RGB pixels = 3 words whose byte pattern repeats every 12 bytes), single pixels at the ragged ends */
 template <int PIX, int W>
-__device__ __forceinline__ void paint_small(typename PixT<PIX>::T *canvas, int r0, const Clip &c, uint32_t val) {
-  if (PIX == 1) {
-    const uint32_t v4 = (val & 255u) * 0x01010101u;
-    const int xa = min((c.x0 + 3) & ~3, c.x1), xb = max(c.x1 & ~3, xa);
-    for (int y = c.y0; y < c.y1; y++) {
-      uint8_t *row = reinterpret_cast<uint8_t *>(canvas) + (size_t)(y - r0) * W;
-      for (int x = c.x0; x < xa; x++) row[x] = (uint8_t)val;
-      for (int x = xa; x < xb; x += 4) *reinterpret_cast<uint32_t *>(row + x) = v4;
-      for (int x = xb; x < c.x1; x++) row[x] = (uint8_t)val;
-    }
-  } else {
+__device__ __forceinline__ void paint_small(uint8_t *canvas, int r0, const Clip &c, uint32_t val) {
+  if (PIX == 4) {
     for (int y = c.y0; y < c.y1; y++) {
       uint32_t *row = reinterpret_cast<uint32_t *>(canvas) + (size_t)(y - r0) * W;
       for (int x = c.x0; x < c.x1; x++) row[x] = val;
     }
+    return;
+  }
+  const int xa = min((c.x0 + 3) & ~3, c.x1), xb = max(c.x1 & ~3, xa);
+  const uint32_t w0 = PIX == 1 ? (val & 255u) * 0x01010101u : ((val & 0xffffffu) | (val << 24));
+  const uint32_t w1 = ((val >> 8) & 0xffffu) | (val << 16), w2 = ((val >> 16) & 0xffu) | (val << 8);
+  for (int y = c.y0; y < c.y1; y++) {
+    uint8_t *row = canvas + (size_t)(y - r0) * W * PIX;
+    for (int x = c.x0; x < xa; x++) put_pixel<PIX>(row, x, val);
+    for (int x = xa; x < xb; x += 4) {
+      uint32_t *q = reinterpret_cast<uint32_t *>(row + x * PIX);
+      q[0] = w0;
+      if (PIX == 3) { q[1] = w1; q[2] = w2; }
+    }
+    for (int x = xb; x < c.x1; x++) put_pixel<PIX>(row, x, val);
   }
 }
 
 /* a whole warp paints one primitive (solid or sprite-masked), lanes over its clipped pixels */
 template <int PIX, int W>
-__device__ __forceinline__ void paint_coop(typename PixT<PIX>::T *canvas, int r0, const Clip &c, int qx, int qy, uint32_t val, uint32_t q3,
+__device__ __forceinline__ void paint_coop(uint8_t *canvas, int r0, const Clip &c, int qx, int qy, uint32_t val, uint32_t q3,
                                            const uint32_t *rec, int lane) {
-  typedef typename PixT<PIX>::T P;
   /* lanes tile the rectangle as (32 >> lg) rows x (1 << lg) columns per pass: no divisions, no int<->float
-   * conversions (those run on the quarter-rate XU pipe, which an earlier version of this kernel saturated) */
+   * conversions (those run on the quarter-rate XU pipe) */
   const int nw = c.x1 - c.x0, nh = c.y1 - c.y0;
   const int lg = nw > 16 ? 5 : nw > 8 ? 4 : nw > 4 ? 3 : nw > 2 ? 2 : nw > 1 ? 1 : 0;
   const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
   const int bw = (q3 >> 16) & 255;
   if (bw == 0) {
     for (int xb = cx; xb < nw; xb += cpl)
-      for (int yy = sub; yy < nh; yy += rpp) canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xb] = (P)val;
+      for (int yy = sub; yy < nh; yy += rpp) put_pixel<PIX>(canvas, (size_t)(c.y0 + yy - r0) * W + c.x0 + xb, val);
   } else {
     const uint32_t off = q3 & 0xffffu;
     const uint32_t *rows = (off & TBX_PRIM_STATE) ? rec + (off & 0x7fffu) : d_bank + off;
@@ -140,7 +149,7 @@ __device__ __forceinline__ void paint_coop(typename PixT<PIX>::T *canvas, int r0
       for (int yy = sub; yy < nh; yy += rpp) {
         const int py = c.y0 + yy - qy;
         const int sy_i = sy == 1 ? py : (int)(((uint32_t)py * iy) >> 16);
-        if ((rows[sy_i] >> (bw - 1 - sx_i)) & 1u) canvas[(size_t)(c.y0 + yy - r0) * W + c.x0 + xb] = (P)val;
+        if ((rows[sy_i] >> (bw - 1 - sx_i)) & 1u) put_pixel<PIX>(canvas, (size_t)(c.y0 + yy - r0) * W + c.x0 + xb, val);
       }
     }
   }
@@ -158,7 +167,7 @@ __device__ __forceinline__ void push_rect(int4 *rects, int *n, int4 r) {
  * group.  All threads of the CTA must call this; it ends with a barrier. */
 template <int GAME, int PIX>
 __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
-                                          int base, typename PixT<PIX>::T *canvas, int r0, int r1, int4 *rects, int *n_rects) {
+                                          int base, uint8_t *canvas, int r0, int r1, int4 *rects, int *n_rects) {
   typedef Traits<GAME> T;
   constexpr int W = T::W;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -257,7 +266,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
 
 /* copy rows [r0,r1) of a base frame into the canvas (full initialisation) */
 template <int PIX, int W>
-__device__ __forceinline__ void load_canvas(typename PixT<PIX>::T *canvas, const uint8_t *base, int r0, int r1) {
+__device__ __forceinline__ void load_canvas(uint8_t *canvas, const uint8_t *base, int r0, int r1) {
   const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)r0 * W * PIX);
   uint4 *dst = reinterpret_cast<uint4 *>(canvas);
   const int n16 = (r1 - r0) * W * PIX / 16;
@@ -266,7 +275,7 @@ __device__ __forceinline__ void load_canvas(typename PixT<PIX>::T *canvas, const
 }
 /* undo one env's painting: re-copy the dirty rectangles (whole 16-byte chunks) from the base frame */
 template <int PIX, int W>
-__device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, const uint8_t *base, int r0, int r1, const int4 *rects, int n) {
+__device__ __forceinline__ void restore_canvas(uint8_t *canvas, const uint8_t *base, int r0, int r1, const int4 *rects, int n) {
   if (n > TBX_MAX_RECTS) { load_canvas<PIX, W>(canvas, base, r0, r1); return; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = wid; i < n; i += TBX_NW) {
@@ -279,7 +288,7 @@ __device__ __forceinline__ void restore_canvas(typename PixT<PIX>::T *canvas, co
     for (int ch = cx; ch < nch; ch += cpl)
       for (int yy = sub; yy < nh; yy += rpp) {
         const size_t off = (size_t)(rc.y + yy) * W * PIX + b0 + 16 * ch;
-        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(canvas) + off - (size_t)r0 * W * PIX) = __ldg(reinterpret_cast<const uint4 *>(base + off));
+        *reinterpret_cast<uint4 *>(canvas + off - (size_t)r0 * W * PIX) = __ldg(reinterpret_cast<const uint4 *>(base + off));
       }
   }
 }
@@ -290,12 +299,11 @@ template <int GAME, int MODE, int TX, int TY>
 __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
-  constexpr int PIX = (MODE == 0 || MODE == 1) ? 4 : 1;
-  typedef typename PixT<PIX>::T P;
+  constexpr int PIX = MODE == 0 ? 4 : MODE == 1 ? 3 : 1; /* canvas bytes per pixel = output bytes per pixel */
   extern __shared__ uint4 smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
   uint32_t *recs = reinterpret_cast<uint32_t *>(smem);
-  P *canvas = reinterpret_cast<P *>(smem + a.smem_canvas);
+  uint8_t *canvas = smem + a.smem_canvas;
   int4 *rect_buf = reinterpret_cast<int4 *>(smem + a.smem_rects); /* two lists, used alternately */
   int *rect_n = reinterpret_cast<int *>(rect_buf + 2 * TBX_MAX_RECTS);
   int *env_base = rect_n + 2; /* base frame id of each env of the chunk */
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
         for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
           const bool colok = dxb + c <= dx1;
           const int dx = colok ? dxb + c : dx1;
-          const uint8_t *col = reinterpret_cast<const uint8_t *>(canvas) + __ldg(&plan->xs0[dx]);
+          const uint8_t *col = canvas + __ldg(&plan->xs0[dx]);
           float al[TX];
 #pragma unroll
           for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
@@ -401,24 +409,10 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     return;
   }
 
-  /* ---- native layouts.
-   * gray / RGBA: the painted canvas band IS the output band: it leaves through the TMA engine, one bulk
-   * shared -> global copy per env (cp.async.bulk), no per-thread load/store instructions.
-   * RGB (3 bytes per pixel, the canvas holds 4): outside the dirty rectangles the frame is the base frame, so the
-   * band is first copied global -> global from the PACKED base frame for the whole chunk (a straight, coalesced
-   * 16-byte copy with the chunk's 8 bands in flight), then only the dirty rectangles are packed from the canvas
-   * (groups of 4 pixels -> 12 bytes) and patched in. */
-  constexpr int OPIX = MODE == 0 ? 4 : MODE == 1 ? 3 : 1; /* output bytes per pixel */
+  /* ---- native layouts (gray, packed RGB, RGBA): the canvas holds the output format, so the painted band IS the
+   * output band and leaves through the TMA engine -- one bulk shared -> global copy per env (cp.async.bulk), no
+   * per-thread load/store instructions. */
   const int r0 = blockIdx.y * a.band_rows, r1 = min(H, r0 + a.band_rows);
-  if (MODE == 1) {
-    const int n16 = (r1 - r0) * W * OPIX / 16;
-    for (int j = 0; j < ne; j++) {
-      const uint4 *src = reinterpret_cast<const uint4 *>((env_base[j] ? a.base_out[1] : a.base_out[0]) + (size_t)r0 * W * OPIX);
-      uint4 *dst = reinterpret_cast<uint4 *>(a.dst + (size_t)(e0 + j) * a.frame_bytes + (size_t)r0 * W * OPIX);
-#pragma unroll 4
-      for (int i = tid; i < n16; i += TBX_NT) dst[i] = __ldg(src + i);
-    }
-  }
   int canvas_base = -1;
   for (int j = 0; j < ne; j++) {
     const uint32_t *R = recs + j * RW;
@@ -432,45 +426,20 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     __syncthreads();
     if (tid == 0) rect_n[(j - 1) & 1] = 0;
     paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
-    if (MODE != 1) {
-      /* one bulk shared -> global copy of the painted band through the TMA engine.  Every thread first makes its
-       * canvas writes visible to the async proxy; the canvas may be touched again once the engine has read it. */
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(canvas);
-        const uint32_t nbytes = (uint32_t)((r1 - r0) * W * OPIX);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)r0 * W * OPIX), "r"(saddr), "r"(nbytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-    } else {
-      /* patch the dirty rectangles (the barriers above order these stores after the band's base copy):
-       * groups of 4 pixels (16 B of RGBA in the canvas) -> 12 B */
-      int nr = *n_rects;
-      const bool overflow = nr > TBX_MAX_RECTS;
-      if (overflow) nr = 1;
-      for (int r = wid; r < nr; r += TBX_NW) {
-        const int4 rc = overflow ? make_int4(0, r0, W, r1) : rects[r];
-        if (rc.z <= rc.x) continue;
-        const int nh = rc.w - rc.y;
-        const int g0 = rc.x >> 2, ng = ((rc.z + 3) >> 2) - g0;
-        const int lg = ng > 16 ? 5 : ng > 8 ? 4 : ng > 4 ? 3 : ng > 2 ? 2 : ng > 1 ? 1 : 0;
-        const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
-        for (int xg = cx; xg < ng; xg += cpl)
-          for (int yy = sub; yy < nh; yy += rpp) {
-            const int y = rc.y + yy;
-            const uint4 v = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(canvas) + (size_t)(y - r0) * W)[g0 + xg];
-            uint32_t *d = reinterpret_cast<uint32_t *>(out + (size_t)y * W * 3) + 3 * (g0 + xg);
-            d[0] = __byte_perm(v.x, v.y, 0x4210);
-            d[1] = __byte_perm(v.y, v.z, 0x5421);
-            d[2] = __byte_perm(v.z, v.w, 0x6542);
-          }
-      }
+    /* every thread makes its canvas writes visible to the async proxy; the canvas may be touched again once the
+     * engine has read it */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(canvas);
+      const uint32_t nbytes = (uint32_t)((r1 - r0) * W * PIX);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)r0 * W * PIX), "r"(saddr), "r"(nbytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncthreads(); /* the canvas is restored next */
   }
-  if (MODE != 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* all bands have left */
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* all bands have left */
 }
 
 } /* namespace tbxk */
