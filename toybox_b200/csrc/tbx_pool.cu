@@ -299,7 +299,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
 
 static int align16(int v) { return (v + 15) & ~15; }
 
-template <int GAME, int MODE, int TX, int TY> static int launch_render(const RenderArgs &a, int smem, cudaStream_t s) {
+template <int GAME, int MODE, int TX, int TY> static int launch_render(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, cudaStream_t s) {
   static int configured = 0; /* per instantiation */
   if (configured < smem) {
     const int want = smem > 160 * 1024 ? smem : 160 * 1024;
@@ -311,25 +311,26 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
   int threads = MODE == TBX_OBS_GRAY_AREA ? 128 : 256;
   if (const char *env = getenv("TBX_RENDER_THREADS")) threads = atoi(env); /* tuning: 32, 64, 128 or 256 */
   if (threads != 32 && threads != 64 && threads != 128 && threads != 256) threads = 128;
-  render_kernel<GAME, MODE, TX, TY><<<grid, threads, smem, s>>>(a);
+  static const TbxAreaPlan no_plan = TbxAreaPlan();
+  render_kernel<GAME, MODE, TX, TY><<<grid, threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, plan_host ? *plan_host : no_plan);
   CK(cudaGetLastError());
   return TBX_OK;
 }
 /* INTER_AREA: the smallest instantiated tap counts that cover the plan */
-template <int GAME, int TY> static int launch_area_tx(int tx, const RenderArgs &a, int smem, cudaStream_t s) {
-  if (tx <= 3) return launch_render<GAME, TBX_OBS_GRAY_AREA, 3, TY>(a, smem, s);
-  if (tx <= 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 4, TY>(a, smem, s);
-  return launch_render<GAME, TBX_OBS_GRAY_AREA, 5, TY>(a, smem, s);
+template <int GAME, int TY> static int launch_area_tx(int tx, const RenderArgs &a, const void *c, const TbxAreaPlan *pl, int smem, cudaStream_t s) {
+  if (tx <= 3) return launch_render<GAME, TBX_OBS_GRAY_AREA, 3, TY>(a, c, pl, smem, s);
+  if (tx <= 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 4, TY>(a, c, pl, smem, s);
+  return launch_render<GAME, TBX_OBS_GRAY_AREA, 5, TY>(a, c, pl, smem, s);
 }
-template <int GAME> static int launch_render_mode(int mode, int tx, int ty, const RenderArgs &a, int smem, cudaStream_t s) {
+template <int GAME> static int launch_render_mode(int mode, int tx, int ty, const RenderArgs &a, const void *c, const TbxAreaPlan *pl, int smem, cudaStream_t s) {
   switch (mode) {
-    case TBX_OBS_RGBA: return launch_render<GAME, TBX_OBS_RGBA, 1, 1>(a, smem, s);
-    case TBX_OBS_RGB: return launch_render<GAME, TBX_OBS_RGB, 1, 1>(a, smem, s);
-    case TBX_OBS_GRAY: return launch_render<GAME, TBX_OBS_GRAY, 1, 1>(a, smem, s);
+    case TBX_OBS_RGBA: return launch_render<GAME, TBX_OBS_RGBA, 1, 1>(a, c, pl, smem, s);
+    case TBX_OBS_RGB: return launch_render<GAME, TBX_OBS_RGB, 1, 1>(a, c, pl, smem, s);
+    case TBX_OBS_GRAY: return launch_render<GAME, TBX_OBS_GRAY, 1, 1>(a, c, pl, smem, s);
     default:
-      if (tx > 5 || ty > 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 8, 8>(a, smem, s);
-      if (ty <= 3) return launch_area_tx<GAME, 3>(tx, a, smem, s);
-      return launch_area_tx<GAME, 4>(tx, a, smem, s);
+      if (tx > 5 || ty > 4) return launch_render<GAME, TBX_OBS_GRAY_AREA, 8, 8>(a, c, pl, smem, s);
+      if (ty <= 3) return launch_area_tx<GAME, 3>(tx, a, c, pl, smem, s);
+      return launch_area_tx<GAME, 4>(tx, a, c, pl, smem, s);
   }
 }
 
@@ -354,12 +355,14 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
   int smem_total, tx = 1, ty = 1;
+  const TbxAreaPlan *host_plan = 0;
   if (mode == TBX_OBS_GRAY_AREA) {
     AreaRes *ar = 0;
     r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
     a.base_out[0] = ar->d_base_out[0]; a.base_out[1] = ar->d_base_out[1]; a.plan = ar->d_plan;
     tx = ar->tx; ty = ar->ty;
+    host_plan = &ar->plan;
     /* Bands of output rows: each (chunk, band) CTA keeps only the canvas rows that feed its output rows, which
      * multiplies the number of independent CTAs per SM.  Surplus (zero-weight) taps may read up to TY-1 rows past
      * the band's last real row: the canvas allocation covers them. */
@@ -384,12 +387,12 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
     a.band_rows = (H + nb - 1) / nb;
     a.smem_rects = a.smem_canvas + align16(a.band_rows * W * pix);
   }
-  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 64; /* + list counts and per-env base ids */
+  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 64 + TBX_MAX_BIG * (int)sizeof(uint4); /* + list counts, per-env base ids, the big-primitive queue */
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, smem_total, s);
-  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, ty, a, smem_total, s);
-  return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, ty, a, smem_total, s);
+  if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
+  if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
+  return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
 }
 
 int tbx_read_scalars(tbx_pool *p, int32_t *score, int32_t *lives, int32_t *level, void *stream) {

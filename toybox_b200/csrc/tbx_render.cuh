@@ -36,6 +36,7 @@ namespace tbxk {
 #define TBX_NW ((int)(blockDim.x >> 5))
 #define TBX_EPC 8
 #define TBX_MAX_RECTS 96
+#define TBX_MAX_BIG 64 /* queue of large / sprite primitives of a group painted by several warps */
 
 __device__ const uint32_t d_bank[TBX_BANK_WORDS] = TBX_BANK_INIT;
 /* ceil(65536 / s) for the sprite scale factors s = 1..15 */
@@ -167,7 +168,7 @@ __device__ __forceinline__ void push_rect(int4 *rects, int *n, int4 r) {
  * group.  All threads of the CTA must call this; it ends with a barrier. */
 template <int GAME, int PIX>
 __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
-                                          int base, uint8_t *canvas, int r0, int r1, int4 *rects, int *n_rects) {
+                                          int base, uint8_t *canvas, int r0, int r1, int4 *rects, int *n_rects, uint4 *bigs, int *n_big) {
   typedef Traits<GAME> T;
   constexpr int W = T::W;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -183,7 +184,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
     if (have_prev && (prev_multi || cur_multi) && !prev_nosync) __syncthreads();
     have_prev = true;
     prev_multi = cur_multi;
-    prev_nosync = (gmode & TBX_GROUP_NOSYNC) != 0;
+    prev_nosync = (gmode & TBX_GROUP_NOSYNC) != 0 && !cur_multi; /* a multi-warp group resets its queue: always fenced */
     if (!(gmode & TBX_GROUP_SERIAL)) {
       for (int s0 = gb; s0 < ge; s0 += TBX_NT) {
         const int s = s0 + tid;
@@ -195,10 +196,15 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
         const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 96;
         if (small) paint_small<PIX, W>(canvas, r0, c, val);
-        unsigned big = __ballot_sync(0xffffffffu, ok && !small);
+        const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
+        const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
+        bool deferred = false;
+        if (cur_multi && ok && !small) { /* a group spread over several warps: queue it, every warp takes its share below */
+          const int k = atomicAdd(n_big, 1);
+          if (k < TBX_MAX_BIG) { bigs[k] = make_uint4(w0, w1, val, w3); deferred = true; }
+        }
+        unsigned big = __ballot_sync(0xffffffffu, ok && !small && !deferred);
         if (big) {
-          const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
-          const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
           while (big) {
             const int l = __ffs(big) - 1;
             big &= big - 1;
@@ -226,6 +232,20 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
           slot0 = __shfl_sync(0xffffffffu, slot0, 0);
           const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
           if (ok && slot < TBX_MAX_RECTS) rects[slot] = make_int4(c.x0, c.y0, c.x1, c.y1);
+        }
+      }
+      if (cur_multi) { /* the queued large / sprite primitives of this conflict-free group, one warp each, round robin */
+        __syncthreads();
+        const int nb = min(*n_big, TBX_MAX_BIG);
+        __syncthreads();
+        if (tid == 0) *n_big = 0; /* the next queueing group starts behind a barrier */
+        for (int i = wid; i < nb; i += TBX_NW) {
+          const uint4 q4 = bigs[i];
+          TbxPrim q;
+          q.x = (int16_t)(q4.x & 0xffffu); q.y = (int16_t)(q4.x >> 16); q.w = (int16_t)(q4.y & 0xffffu); q.h = (int16_t)(q4.y >> 16);
+          Clip qc;
+          clip_prim<W>(q, r0, r1, qc);
+          paint_coop<PIX, W>(canvas, r0, qc, q.x, q.y, q4.z, q4.w, R, lane);
         }
       }
     } else if (wid == 0) {
@@ -296,7 +316,11 @@ __device__ __forceinline__ void restore_canvas(uint8_t *canvas, const uint8_t *b
 /* MODE: TBX_OBS_RGBA (0), TBX_OBS_RGB (1), TBX_OBS_GRAY (2), TBX_OBS_GRAY_AREA (3).
  * TX, TY: taps per output column / row of the INTER_AREA plan (>= plan.tx, plan.ty; surplus taps have zero weight). */
 template <int GAME, int MODE, int TX, int TY>
-__global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) render_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ typename Traits<GAME>::Cfg cfg_c,
+                                                                                          const __grid_constant__ TbxAreaPlan plan_c) {
+  /* The pool's config and the INTER_AREA plan travel as kernel parameters: warp-uniform reads of them (colours,
+   * row taps, inverse maps) come from the constant bank instead of global memory.  Reads indexed per lane (column
+   * taps) still go through `a.plan` in global memory / L1, where they coalesce. */
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
   constexpr int PIX = MODE == 0 ? 4 : MODE == 1 ? 3 : 1; /* canvas bytes per pixel = output bytes per pixel */
@@ -307,7 +331,9 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
   int4 *rect_buf = reinterpret_cast<int4 *>(smem + a.smem_rects); /* two lists, used alternately */
   int *rect_n = reinterpret_cast<int *>(rect_buf + 2 * TBX_MAX_RECTS);
   int *env_base = rect_n + 2; /* base frame id of each env of the chunk */
-  const typename T::Cfg &cfg = *(const typename T::Cfg *)a.cfg;
+  int *n_big = env_base + TBX_EPC;
+  uint4 *big_buf = reinterpret_cast<uint4 *>(rect_n + 16);
+  const typename T::Cfg &cfg = cfg_c;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
@@ -319,6 +345,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
   }
   if (tid < 2) rect_n[tid] = 0;
+  if (tid == 2) *n_big = 0;
   __syncthreads();
 
   if (tid < ne) env_base[tid] = T::base_id(recs + tid * RW, cfg, tables);
@@ -326,10 +353,11 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
 
   if constexpr (MODE == 3) {
     const TbxAreaPlan *__restrict__ plan = a.plan;
-    const int dw = plan->dw, dh = plan->dh;
+    const TbxAreaPlan &cplan = plan_c;
+    const int dw = cplan.dw, dh = cplan.dh;
     /* this CTA's band: output rows [d0,d1) and the canvas rows [r0,r1) that feed them (TY taps per output row) */
     const int d0 = blockIdx.y * a.band_rows, d1 = min(dh, d0 + a.band_rows);
-    const int r0 = __ldg(&plan->ys0[d0]), r1 = min(H, (int)__ldg(&plan->ys0[d1 - 1]) + TY);
+    const int r0 = cplan.ys0[d0], r1 = min(H, (int)cplan.ys0[d1 - 1] + TY);
     /* the static part of the band in every output frame of the chunk: the base frame's down-sample, global ->
      * global (16-, 4- or 1-byte units, whatever the band's byte range allows) */
     {
@@ -359,7 +387,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
       canvas_base = base;
       __syncthreads();
       if (tid == 0) rect_n[(j - 1) & 1] = 0; /* that list is reused by env j+1 */
-      paint_env<GAME, 1>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
+      paint_env<GAME, 1>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects, big_buf, n_big);
       /* Recompute the band's output pixels fed by a dirty rectangle and patch them into the destination frame
        * (the barriers above order these byte stores after the band's base copy).  Lanes own output columns (their
        * taps stay in registers), warps own output rows; narrow rectangles pack several rows into one warp.
@@ -375,8 +403,8 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
         const bool shared = (rc.z - rc.x) * (rc.w - rc.y) > 400;
         if (!shared && (r & (TBX_NW - 1)) != wid) continue;
         const int wsel = shared ? wid : 0, wcnt = shared ? TBX_NW : 1;
-        const int dx0 = __ldg(&plan->xdlo[rc.x]), dx1 = __ldg(&plan->xdhi[rc.z - 1]);
-        const int dy0 = max((int)__ldg(&plan->ydlo[rc.y]), d0), dy1 = min((int)__ldg(&plan->ydhi[rc.w - 1]), d1 - 1);
+        const int dx0 = cplan.xdlo[rc.x], dx1 = cplan.xdhi[rc.z - 1];
+        const int dy0 = max((int)cplan.ydlo[rc.y], d0), dy1 = min((int)cplan.ydhi[rc.w - 1], d1 - 1);
         if (dy0 > dy1) continue;
         const int ncols = dx1 - dx0 + 1;
         const int lg = ncols > 16 ? 5 : ncols > 8 ? 4 : ncols > 4 ? 3 : 2; /* columns per warp pass = 1 << lg */
@@ -389,14 +417,14 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
 #pragma unroll
           for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
           for (int dy = dy0 + wsel * rpi + sub; dy <= dy1; dy += wcnt * rpi) {
-            const uint8_t *row = col + (size_t)((int)__ldg(&plan->ys0[dy]) - r0) * W;
+            const uint8_t *row = col + (size_t)((int)cplan.ys0[dy] - r0) * W;
             float v = 0.0f;
 #pragma unroll
             for (int k = 0; k < TY; k++) {
               float h = tbx_fmul(tbx_u8f(row[k * W]), al[0]);
 #pragma unroll
               for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(row[k * W + t]), al[t]));
-              const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+              const float bh = tbx_fmul(cplan.yalpha[k][dy], h);
               v = k == 0 ? bh : tbx_fadd(v, bh);
             }
             const int iv = tbx_f2i_rn_small(v);
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     canvas_base = base;
     __syncthreads();
     if (tid == 0) rect_n[(j - 1) & 1] = 0;
-    paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects);
+    paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects, big_buf, n_big);
     /* every thread makes its canvas writes visible to the async proxy; the canvas may be touched again once the
      * engine has read it */
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
