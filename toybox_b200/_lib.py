@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libtoybox_b200.so")
+_SO = os.environ.get("TBX_LIB_PATH") or os.path.join(_HERE, "libtoybox_b200.so")   # TBX_LIB_PATH: tuning builds
 _CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 

@@ -6,6 +6,7 @@
 #define TBX_KERNELS_CUH
 #include <cuda_runtime.h>
 #include "tbx_render.cuh"
+#include "tbx_render_area.cuh"
 #include "tbx_host.h"
 
 namespace tbxk {

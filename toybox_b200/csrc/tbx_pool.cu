@@ -4,6 +4,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <string.h>
 #include <vector>
 
 using namespace tbxk;
@@ -316,6 +317,27 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
   CK(cudaGetLastError());
   return TBX_OK;
 }
+/* INTER_AREA, one warp per env (tbx_render_area.cuh) */
+template <int GAME, int TX, int TY> static int launch_area_tile(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
+  static int configured = 0;
+  if (configured < smem) {
+    CK((cudaFuncSetAttribute(area_tile_kernel<GAME, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    configured = smem;
+  }
+  area_tile_kernel<GAME, TX, TY><<<blocks(a.n, TBX_EPC), threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, *plan_host);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+template <int GAME> static int launch_area_tile_taps(int tx, int ty, const RenderArgs &a, const void *c, const TbxAreaPlan *pl, int smem, int threads, cudaStream_t s) {
+  if (ty <= 3) {
+    if (tx <= 3) return launch_area_tile<GAME, 3, 3>(a, c, pl, smem, threads, s);
+    if (tx <= 4) return launch_area_tile<GAME, 4, 3>(a, c, pl, smem, threads, s);
+    return launch_area_tile<GAME, 5, 3>(a, c, pl, smem, threads, s);
+  }
+  if (tx <= 3) return launch_area_tile<GAME, 3, 4>(a, c, pl, smem, threads, s);
+  if (tx <= 4) return launch_area_tile<GAME, 4, 4>(a, c, pl, smem, threads, s);
+  return launch_area_tile<GAME, 5, 4>(a, c, pl, smem, threads, s);
+}
 /* INTER_AREA: the smallest instantiated tap counts that cover the plan */
 template <int GAME, int TY> static int launch_area_tx(int tx, const RenderArgs &a, const void *c, const TbxAreaPlan *pl, int smem, cudaStream_t s) {
   if (tx <= 3) return launch_render<GAME, TBX_OBS_GRAY_AREA, 3, TY>(a, c, pl, smem, s);
@@ -348,7 +370,7 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   const int pix = mode == TBX_OBS_RGBA ? 4 : mode == TBX_OBS_RGB ? 3 : 1; /* canvas bytes per pixel */
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
-  a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h;
+  a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h; a.tile_stride = 0; a.warp_bytes = 0; a.list_cap = 0; a.tile_hshift = 0; a.max_run = 0; a.band_rows = 0; a.smem_rects = 0;
   for (int b = 0; b < 2; b++) {
     a.base[b] = pix == 4 ? p->d_base_rgba[b] : pix == 3 ? p->d_base_rgb[b] : p->d_base_gray[b];
     a.base_out[b] = 0; /* INTER_AREA: set below */
@@ -367,6 +389,46 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
      * multiplies the number of independent CTAs per SM.  Surplus (zero-weight) taps may read up to TY-1 rows past
      * the band's last real row: the canvas allocation covers them. */
     const int ty_inst = (tx > 5 || ty > 4) ? 8 : (ty <= 3 ? 3 : 4);
+    /* default: one warp per env over 16x4 output tiles; plans with many taps (or TBX_AREA_KERNEL=cta) use the
+     * CTA-wide canvas kernel below */
+    const char *ksel = getenv("TBX_AREA_KERNEL");
+    if (tx <= 5 && ty <= 4 && !(ksel && !strcmp(ksel, "cta"))) {
+      const int tx_inst = tx <= 3 ? 3 : tx <= 4 ? 4 : 5;
+      /* tiles of 16 x 8 output pixels, runs of at most 3 tiles: the scratch holds the widest / tallest run window */
+      int ths = 3, max_run = 3;
+      if (const char *env = getenv("TBX_AREA_TILE_H")) ths = atoi(env) == 4 ? 2 : 3;
+      if (const char *env = getenv("TBX_AREA_MAX_RUN")) max_run = atoi(env);
+      if (max_run < 1) max_run = 1;
+      if (max_run > 8) max_run = 8;
+      int stride = 0, rows = 0;
+      for (int dxA = 0; dxA < out_w; dxA += 16) {
+        const int dxL = dxA + 16 * max_run - 1 < out_w ? dxA + 16 * max_run - 1 : out_w - 1;
+        const int wdt = ((ar->plan.xs0[dxL] + tx_inst + 3) & ~3) - (ar->plan.xs0[dxA] & ~3);
+        if (wdt > stride) stride = wdt;
+      }
+      for (int dyA = 0; dyA < out_h; dyA += 1 << ths) {
+        const int dyL = dyA + (1 << ths) - 1 < out_h ? dyA + (1 << ths) - 1 : out_h - 1;
+        const int rws = ar->plan.ys0[dyL] + ty_inst - ar->plan.ys0[dyA];
+        if (rws > rows) rows = rws;
+      }
+      if (stride <= 512 && rows <= 96 && W % 4 == 0) {
+        int threads = 256;
+        if (const char *env = getenv("TBX_AREA_THREADS")) threads = atoi(env);
+        if (threads != 32 && threads != 64 && threads != 128 && threads != 256) threads = 256;
+        a.tile_stride = stride;
+        a.tile_hshift = ths;
+        a.max_run = max_run;
+        a.list_cap = TBX_TILE_LCAP;
+        if (const char *env = getenv("TBX_AREA_LCAP")) a.list_cap = atoi(env); /* tests: small lists force the sweep / per-tile paths */
+        if (a.list_cap < 1 || a.list_cap > TBX_TILE_LCAP) a.list_cap = TBX_TILE_LCAP;
+        a.warp_bytes = align16(TBX_TILE_LCAP * 20 + 32 + stride * rows);
+        const int smem = a.smem_canvas + (threads / 32) * a.warp_bytes;
+        cudaStream_t s = (cudaStream_t)stream;
+        if (p->game == TBX_BREAKOUT) return launch_area_tile_taps<TBX_BREAKOUT>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
+        if (p->game == TBX_AMIDAR) return launch_area_tile_taps<TBX_AMIDAR>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
+        return launch_area_tile_taps<TBX_SPACE_INVADERS>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
+      }
+    }
     int nb = p->game == TBX_AMIDAR ? 1 : 2;
     if (const char *env = getenv("TBX_AREA_BANDS")) nb = atoi(env);
     if (nb < 1) nb = 1;

@@ -83,6 +83,7 @@ struct RenderArgs {
   int band_rows;              /* per CTA (blockIdx.y selects the band): canvas rows (native layouts) / output rows (INTER_AREA) */
   int out_h;                  /* INTER_AREA: output rows (host-side launch geometry) */
   int smem_canvas, smem_rects; /* byte offsets into dynamic shared memory */
+  int tile_stride, warp_bytes, list_cap, tile_hshift, max_run; /* INTER_AREA tile kernel (tbx_render_area.cuh): scratch row pitch, shared memory per warp */
 };
 
 /* The canvas is a byte array with PIX bytes per pixel: 1 = gray, 3 = packed RGB, 4 = RGBA.  `val` is the colour

@@ -1,0 +1,376 @@
+/* tbx_render_area.cuh -- the INTER_AREA (WarpFrame, e.g. 84x84 gray) render kernel: ONE WARP PER ENV, tile based.
+ *
+ * The reference produces this observation as get_state() (native gray frame, toybox/envs/atari/base.py:109)
+ * followed by cv2.resize(..., INTER_AREA) (baselines/baselines/common/atari_wrappers.py:243).  An output frame is
+ * only 7 KB, so a CTA-wide shared canvas with barriers between the phases of every env (tbx_render.cuh, still used
+ * for the native layouts) leaves most issue slots idle.  Here a warp renders its env alone -- no CTA barrier after
+ * the record load -- and never materialises the native frame:
+ *   1. the pre-computed down-sample of the env's base frame is copied to the destination (16-byte units);
+ *   2. the draw-list entries that differ from the base frame are built once (32 slots per pass, one per lane) and
+ *      appended, in draw order, to a per-warp list in shared memory; every entry marks the OUTPUT TILES (16 x 4
+ *      output pixels) its pixels feed;
+ *   3. for every run of horizontally adjacent marked tiles the warp copies the run's source window of the base
+ *      frame (a few source rows) into a small shared-memory scratch canvas, paints the list entries that touch it in draw order (painter's
+ *      algorithm, identical result to painting the whole frame), and recomputes the tile's output rows that those
+ *      entries feed with cv2's exact f32 tap order; the bytes are patched into the destination frame.
+ * If an env has more entries than the list holds, its output rows are processed in 2, 4, ... sweeps, each with the
+ * entries clipped to the sweep's source rows; if even one tile row overflows, that row is rendered by re-building
+ * the primitives per tile (slow, but always correct).
+ * Members of a PARALLEL draw-list group cannot conflict, so inside a tile the small solid ones (bricks, maze tiles)
+ * are painted lane-parallel; everything else is painted by the whole warp, one entry at a time, in draw order.
+ */
+#ifndef TBX_RENDER_AREA_CUH
+#define TBX_RENDER_AREA_CUH
+#include "tbx_render.cuh"
+
+namespace tbxk {
+
+#define TBX_TILE_LCAP 128 /* list entries per warp */
+#define TBX_AREA_MAX_THREADS 256
+#ifndef TBX_AREA_MIN_CTAS
+#define TBX_AREA_MIN_CTAS 4
+#endif
+
+/* a warp paints one primitive into the tile scratch canvas: window columns [wx0, wx1) (wx0 a multiple of 4, the
+ * scratch's column 0), rows [wy0, wy1); `stride` bytes per scratch row */
+__device__ __forceinline__ void paint_tile(uint8_t *tile, int stride, int wx0, int wy0, int wx1, int wy1, int qx, int qy, int qw, int qh,
+                                           uint32_t val, uint32_t q3, const uint32_t *rec, int lane) {
+  const int x0 = max(qx, wx0), x1 = min(qx + qw, wx1), y0 = max(qy, wy0), y1 = min(qy + qh, wy1);
+  const int nw = x1 - x0, nh = y1 - y0;
+  if (nw <= 0 || nh <= 0) return;
+  const int lg = nw > 16 ? 5 : nw > 8 ? 4 : nw > 4 ? 3 : nw > 2 ? 2 : nw > 1 ? 1 : 0;
+  const int cpl = 1 << lg, rpp = 32 >> lg, sub = lane >> lg, cx = lane & (cpl - 1);
+  const int bw = (q3 >> 16) & 255;
+  uint8_t *org = tile + (y0 - wy0) * stride + (x0 - wx0);
+  if (bw == 0) {
+    for (int yy = sub; yy < nh; yy += rpp)
+      for (int xb = cx; xb < nw; xb += cpl) org[yy * stride + xb] = (uint8_t)val;
+  } else {
+    const uint32_t off = q3 & 0xffffu;
+    const bool state = (off & TBX_PRIM_STATE) != 0; /* sprite rows in the env's record (shared) or in the bank (global) */
+    const int o = state ? (int)(off & 0x7fffu) : (int)off;
+    const int sx = (q3 >> 24) & 15, sy = q3 >> 28;
+    const uint32_t ix = d_inv16[sx], iy = d_inv16[sy];
+    for (int yy = sub; yy < nh; yy += rpp) {
+      const int py = y0 + yy - qy;
+      const int sy_i = sy == 1 ? py : (int)(((uint32_t)py * iy) >> 16);
+      const uint32_t bits = state ? rec[o + sy_i] : __ldg(&d_bank[o + sy_i]);
+      for (int xb = cx; xb < nw; xb += cpl) {
+        const int px = x0 + xb - qx;
+        const int sx_i = sx == 1 ? px : (int)(((uint32_t)px * ix) >> 16);
+        if ((bits >> (bw - 1 - sx_i)) & 1u) org[yy * stride + xb] = (uint8_t)val;
+      }
+    }
+  }
+}
+
+/* list entry (uint4) + extent word:
+ *   x: x | y << 16;  y: w | h << 16;  z: gray | group << 8 | flags << 16;  w: sprite off | bw << 16 | scale << 24
+ *   extent: dxlo | dxhi << 8 | dylo << 16 | dyhi << 24 = the output columns / rows the (clipped) primitive feeds.
+ * flags: ENTRY_PAR = member of a PARALLEL draw-list group (no two members conflict, any paint order is right);
+ *        ENTRY_SMALL = solid rectangle of at most 256 pixels (one lane paints it alone). */
+#define TBX_ENTRY_PAR 1u
+#define TBX_ENTRY_SMALL 2u
+template <int W>
+__device__ __forceinline__ bool make_entry(const TbxPrim &p, int g, int gmode, int rA, int rB, int dyA, int dyB, const TbxAreaPlan *__restrict__ plan,
+                                           uint4 &e, uint32_t &ext) {
+  Clip c;
+  if (!clip_prim<W>(p, rA, rB, c)) return false;
+  const int dylo = max((int)__ldg(&plan->ydlo[c.y0]), dyA), dyhi = min((int)__ldg(&plan->ydhi[c.y1 - 1]), dyB - 1);
+  if (dylo > dyhi) return false;
+  const int dxlo = __ldg(&plan->xdlo[c.x0]), dxhi = __ldg(&plan->xdhi[c.x1 - 1]);
+  const uint32_t flags = ((gmode & TBX_GROUP_SERIAL) ? 0u : TBX_ENTRY_PAR) | ((p.bw == 0 && (int)p.w * (int)p.h <= 256) ? TBX_ENTRY_SMALL : 0u);
+  e.x = (uint32_t)(uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16);
+  e.y = (uint32_t)(uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
+  e.z = tbx_luma(p.color) | ((uint32_t)g << 8) | (flags << 16);
+  e.w = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
+  ext = (uint32_t)dxlo | ((uint32_t)dxhi << 8) | ((uint32_t)dylo << 16) | ((uint32_t)dyhi << 24);
+  return true;
+}
+/* tiles (16 x (1 << ths) output pixels) are numbered 8 per tile row: bit (ty & 3) * 8 + tx of word ty >> 2 */
+__device__ __forceinline__ void mark_tiles(uint32_t *tmask, uint32_t ext, int ths) {
+  const int txlo = (ext & 255u) >> 4, txhi = ((ext >> 8) & 255u) >> 4, tylo = ((ext >> 16) & 255u) >> ths, tyhi = (ext >> 24) >> ths;
+  const uint32_t cols = ((2u << (txhi - txlo)) - 1u) << txlo;
+  for (int ty = tylo; ty <= tyhi; ty++) atomicOr(&tmask[ty >> 2], cols << ((ty & 3) * 8));
+}
+
+/* one lane fills its own small solid rectangle in the tile scratch: 32-bit stores over the aligned middle of a row */
+__device__ __forceinline__ void paint_tile_lane(uint8_t *tile, int stride, int wx0, int wy0, int wx1, int wy1, int qx, int qy, int qw, int qh, uint32_t val) {
+  const int x0 = max(qx, wx0) - wx0, x1 = min(qx + qw, wx1) - wx0, y0 = max(qy, wy0) - wy0, y1 = min(qy + qh, wy1) - wy0;
+  if (x0 >= x1 || y0 >= y1) return;
+  const int xa = min((x0 + 3) & ~3, x1), xb = max(x1 & ~3, xa);
+  const uint32_t w4 = (val & 255u) * 0x01010101u;
+  for (int y = y0; y < y1; y++) {
+    uint8_t *row = tile + y * stride;
+    for (int x = x0; x < xa; x++) row[x] = (uint8_t)val;
+    for (int x = xa; x < xb; x += 4) *reinterpret_cast<uint32_t *>(row + x) = w4;
+    for (int x = xb; x < x1; x++) row[x] = (uint8_t)val;
+  }
+}
+
+/* copy the source window [wx0,wx1) x [wy0,wy1) of the base frame into the scratch (wx0, wx1 multiples of 4) */
+template <int W>
+__device__ __forceinline__ void tile_load(uint8_t *tile, int stride, const uint8_t *bfr, int wx0, int wy0, int wx1, int wy1, int lane) {
+  const int nwr = (wx1 - wx0) >> 2, nrows = wy1 - wy0;
+  const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
+  const int rstep = 32 >> lg;
+  for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32) { /* one trip unless the window is wider than 128 bytes */
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(bfr + (size_t)wy0 * W + wx0) + cc + (lane >> lg) * (W >> 2);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(tile) + cc + (lane >> lg) * (stride >> 2);
+    for (int y = lane >> lg; y < nrows; y += rstep, src += rstep * (W >> 2), dst += rstep * (stride >> 2)) *dst = __ldg(src);
+  }
+}
+
+/* recompute output pixels [dx0,dx1] x [dy0,dy1] from the scratch and patch them into the frame: TX x TY taps in cv2's
+ * order; surplus taps carry zero weights and may read scratch bytes outside the copied window (x + 0*b == x here) */
+template <int TX, int TY>
+__device__ __forceinline__ void tile_resolve(const uint8_t *tile, int stride, int wx0, int wy0, int dx0, int dx1, int dy0, int dy1, int dw,
+                                             const TbxAreaPlan *__restrict__ plan, uint8_t *out, int lane) {
+  const int ncol = dx1 - dx0 + 1;
+  const int lg = ncol > 16 ? 5 : ncol > 8 ? 4 : ncol > 4 ? 3 : 2;
+  const int c = lane & ((1 << lg) - 1), cpl = 1 << lg, rstep = 32 >> lg;
+  for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
+    const int dx = dxb + c;
+    const bool colok = dx <= dx1;
+    const int dxc = colok ? dx : dx1;
+    const uint8_t *col = tile + ((int)__ldg(&plan->xs0[dxc]) - wx0);
+    float al[TX];
+#pragma unroll
+    for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dxc]);
+    for (int dy = dy0 + (lane >> lg); dy <= dy1; dy += rstep) {
+      const uint8_t *row = col + ((int)__ldg(&plan->ys0[dy]) - wy0) * stride;
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        float h = tbx_fmul(tbx_u8f(row[k * stride]), al[0]);
+#pragma unroll
+        for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(row[k * stride + t]), al[t]));
+        const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+        v = k == 0 ? bh : tbx_fadd(v, bh);
+      }
+      const int iv = tbx_f2i_rn_small(v);
+      if (colok) out[dy * dw + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+    }
+  }
+}
+
+__device__ __forceinline__ void paint_entry_coop(uint8_t *tile, int stride, int wx0, int wy0, int wx1, int wy1, const uint4 &q, const uint32_t *R, int lane) {
+  paint_tile(tile, stride, wx0, wy0, wx1, wy1, (int16_t)(q.x & 0xffffu), (int16_t)(q.x >> 16), (int16_t)(q.y & 0xffffu), (int16_t)(q.y >> 16),
+             q.z & 255u, q.w, R, lane);
+}
+
+/* One tile row with more entries than the list holds: every tile of the row re-builds the primitives and paints
+ * those that touch it, strictly in draw order (slow, but always correct). */
+template <int GAME, int TX, int TY>
+__device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables, int base,
+                                              const uint8_t *bfr, const TbxAreaPlan *__restrict__ plan, const TbxAreaPlan &cp, uint8_t *tile, int stride,
+                                              int ty, int ths, int rA, int rB, int dyA, int dyB, uint8_t *out, int lane) {
+  typedef Traits<GAME> T;
+  constexpr int W = T::W, H = T::H;
+  const int dw = cp.dw, dh = cp.dh;
+  const int dy0 = ty << ths, dy1 = min(dy0 + (1 << ths) - 1, dh - 1);
+  const int wy0 = cp.ys0[dy0], wy1 = min(H, (int)cp.ys0[dy1] + TY);
+  for (int dxA = 0; dxA < dw; dxA += 16) {
+    const int dxL = min(dxA + 15, dw - 1);
+    const int wx0 = cp.xs0[dxA] & ~3, wx1 = min(W, ((int)cp.xs0[dxL] + TX + 3) & ~3);
+    tile_load<W>(tile, stride, bfr, wx0, wy0, wx1, wy1, lane);
+    __syncwarp();
+    for (int g = 0; g < T::NG; g++) {
+      int gb, ge, gmode;
+      T::group(g, R, tables, base, gb, ge, gmode);
+      for (int s0 = gb; s0 < ge; s0 += 32) {
+        const int s = s0 + lane;
+        TbxPrim p = tbx_prim_none();
+        if (s < ge) p = T::prim(R, cfg, tables, s, base);
+        uint4 e;
+        uint32_t ext;
+        bool hit = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
+        hit = hit && (int)(ext & 255u) <= dxL && (int)((ext >> 8) & 255u) >= dxA;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          uint4 q;
+          q.x = __shfl_sync(0xffffffffu, e.x, l); q.y = __shfl_sync(0xffffffffu, e.y, l);
+          q.z = __shfl_sync(0xffffffffu, e.z, l); q.w = __shfl_sync(0xffffffffu, e.w, l);
+          paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
+          __syncwarp();
+        }
+      }
+    }
+    tile_resolve<TX, TY>(tile, stride, wx0, wy0, dxA, dxL, dy0, dy1, dw, plan, out, lane);
+    __syncwarp();
+  }
+}
+
+template <int GAME, int TX, int TY>
+__global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_tile_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ typename Traits<GAME>::Cfg cfg_c,
+                                                                         const __grid_constant__ TbxAreaPlan plan_c) {
+  typedef Traits<GAME> T;
+  constexpr int W = T::W, H = T::H, RW = T::RW;
+  extern __shared__ uint4 smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
+  uint32_t *recs = reinterpret_cast<uint32_t *>(smem);
+  const typename T::Cfg &cfg = cfg_c;
+  const typename T::Table *tables = (const typename T::Table *)a.tables;
+  const TbxAreaPlan *__restrict__ plan = a.plan; /* per-lane indexed reads: global memory / L1 */
+  const TbxAreaPlan &cp = plan_c;                /* warp-uniform reads: constant bank */
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+  const int e0 = blockIdx.x * TBX_EPC;
+  const int ne = min(TBX_EPC, a.n - e0);
+  for (int i = tid; i < RW * TBX_EPC; i += blockDim.x) {
+    const int w = i / TBX_EPC, j = i - w * TBX_EPC;
+    if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
+  }
+  __syncthreads(); /* the only CTA barrier: from here on every warp works alone */
+
+  uint8_t *wmem = smem + a.smem_canvas + wid * a.warp_bytes;
+  uint4 *list = reinterpret_cast<uint4 *>(wmem);
+  uint32_t *exts = reinterpret_cast<uint32_t *>(wmem + TBX_TILE_LCAP * 16);
+  uint32_t *tmask = exts + TBX_TILE_LCAP;
+  uint8_t *tile = reinterpret_cast<uint8_t *>(tmask + 8);
+  const int stride = a.tile_stride;
+  const int ths = a.tile_hshift; /* tiles are 16 x (1 << ths) output pixels */
+  const int dw = cp.dw, dh = cp.dh, nty = (dh + (1 << ths) - 1) >> ths;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  for (int j = wid; j < ne; j += nwarps) {
+    const uint32_t *R = recs + j * RW;
+    const int base = T::base_id(R, cfg, tables);
+    const uint8_t *bfr = base ? a.base[1] : a.base[0];
+    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    { /* 1. the static part of the frame */
+      const uint8_t *src = base ? a.base_out[1] : a.base_out[0];
+      const int nb = dw * dh;
+      if ((a.frame_bytes & 15) == 0) {
+        for (int i = lane; i < (nb >> 4); i += 32) reinterpret_cast<uint4 *>(out)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+      } else if ((a.frame_bytes & 3) == 0) {
+        for (int i = lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t *>(out)[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+      } else {
+        for (int i = lane; i < nb; i += 32) out[i] = __ldg(src + i);
+      }
+    }
+    __syncwarp(); /* orders the base copy before the patches other lanes write below */
+
+    int nsw = 1;
+    for (int sw = 0; sw < nsw; sw++) {
+      /* this sweep: tile rows [tyA, tyB), output rows [dyA, dyB), source rows [rA, rB) */
+      const int tyA = (sw * nty) / nsw, tyB = ((sw + 1) * nty) / nsw;
+      if (tyA >= tyB) continue;
+      const int dyA = tyA << ths, dyB = min(dh, tyB << ths);
+      const int rA = cp.ys0[dyA], rB = min(H, (int)cp.ys0[dyB - 1] + TY);
+      /* 2. build the sweep's list */
+      __syncwarp();
+      if (lane < 8) tmask[lane] = 0;
+      __syncwarp();
+      int n = 0;
+      bool overflow = false;
+      for (int g = 0; g < T::NG && !overflow; g++) {
+        int gb, ge, gmode;
+        T::group(g, R, tables, base, gb, ge, gmode);
+        for (int s0 = gb; s0 < ge; s0 += 32) {
+          const int s = s0 + lane;
+          TbxPrim p = tbx_prim_none();
+          if (s < ge) p = T::prim(R, cfg, tables, s, base);
+          uint4 e;
+          uint32_t ext;
+          const bool ok = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (m == 0) continue;
+          if (n + __popc(m) > a.list_cap) { overflow = true; break; }
+          if (ok) {
+            const int slot = n + __popc(m & lt_mask);
+            list[slot] = e;
+            exts[slot] = ext;
+            mark_tiles(tmask, ext, ths);
+          }
+          n += __popc(m);
+        }
+      }
+      if (overflow && nsw < nty) { /* halve the sweeps' height and start over (finished tiles are simply redone) */
+        nsw = min(nty, nsw * 2);
+        sw = -1;
+        continue;
+      }
+      __syncwarp();
+
+      if (overflow) {
+        tile_row_rebuild<GAME, TX, TY>(R, cfg, tables, base, bfr, plan, cp, tile, stride, tyA, ths, rA, rB, dyA, dyB, out, lane);
+        continue;
+      }
+      if (n == 0) continue;
+
+      /* 3. the marked tiles, one RUN of horizontally adjacent marked tiles of a tile row at a time.  Lanes hold the
+       * extents of the entries (32 per chunk, one per lane), so "which entries feed this run, and which of its pixels" is one
+       * compare per lane, a ballot and four warp reductions. */
+      for (int ty = tyA; ty < tyB; ty++) {
+        uint32_t rowbits = (tmask[ty >> 2] >> ((ty & 3) * 8)) & 0xffu;
+        while (rowbits) {
+          const int t0 = __ffs(rowbits) - 1;
+          const int len = min(__ffs(~(rowbits >> t0)) - 1, a.max_run); /* consecutive marked tiles */
+          rowbits &= ~(((1u << len) - 1u) << t0);
+          const int rx0 = t0 * 16, rx1 = rx0 + len * 16 - 1, ry0 = ty << ths, ry1 = ry0 + (1 << ths) - 1;
+          uint32_t hm[TBX_TILE_LCAP / 32];
+          int bx0 = 255, bx1 = 0, by0 = 255, by1 = 0;
+#pragma unroll
+          for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
+            hm[c] = 0;
+            if (c * 32 >= n) continue;
+            const uint32_t ext = c * 32 + lane < n ? exts[c * 32 + lane] : 0x000000ffu; /* 0xff: never hit */
+            const int xlo = ext & 255u, xhi = (ext >> 8) & 255u, ylo = (ext >> 16) & 255u, yhi = ext >> 24;
+            const bool hit = xlo <= rx1 && xhi >= rx0 && ylo <= ry1 && yhi >= ry0;
+            hm[c] = __ballot_sync(0xffffffffu, hit);
+            if (hit) { bx0 = min(bx0, xlo); bx1 = max(bx1, xhi); by0 = min(by0, ylo); by1 = max(by1, yhi); }
+          }
+          const int dx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)), dx1 = min(rx1, __reduce_max_sync(0xffffffffu, bx1));
+          const int dy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), dy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
+          if (dx0 > dx1 || dy0 > dy1) continue;
+          const int wx0 = cp.xs0[dx0] & ~3, wx1 = min(W, ((int)cp.xs0[dx1] + TX + 3) & ~3);
+          const int wy0 = cp.ys0[dy0], wy1 = min(H, (int)cp.ys0[dy1] + TY);
+          tile_load<W>(tile, stride, bfr, wx0, wy0, wx1, wy1, lane);
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
+            uint32_t m = hm[c];
+            if (m == 0) continue;
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if ((m >> lane) & 1u) e = list[c * 32 + lane];
+            while (m) {
+              const int l = __ffs(m) - 1;
+              const uint32_t zl = __shfl_sync(0xffffffffu, e.z, l);
+              if (!((zl >> 16) & TBX_ENTRY_PAR)) { /* in-order group: one entry at a time */
+                const uint4 q = list[c * 32 + l];
+                paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
+                __syncwarp();
+                m &= m - 1;
+                continue;
+              }
+              /* every hit entry of the same conflict-free group: the small solid ones lane-parallel, the rest one by one */
+              const bool mine = ((m >> lane) & 1u) && ((e.z >> 8) & 255u) == ((zl >> 8) & 255u);
+              const uint32_t same = __ballot_sync(0xffffffffu, mine);
+              const bool small = mine && ((e.z >> 16) & TBX_ENTRY_SMALL);
+              uint32_t big = same & ~__ballot_sync(0xffffffffu, small);
+              if (small)
+                paint_tile_lane(tile, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
+                                (int16_t)(e.y >> 16), e.z & 255u);
+              __syncwarp();
+              while (big) {
+                const int lb = __ffs(big) - 1;
+                big &= big - 1;
+                const uint4 q = list[c * 32 + lb];
+                paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
+                __syncwarp();
+              }
+              m &= ~same;
+            }
+          }
+          tile_resolve<TX, TY>(tile, stride, wx0, wy0, dx0, dx1, dy0, dy1, dw, plan, out, lane);
+          __syncwarp(); /* the scratch canvas is overwritten by the next run */
+        }
+      }
+    }
+  }
+}
+
+} /* namespace tbxk */
+#endif
