@@ -100,13 +100,42 @@ def reference_arm(args):
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every 2 ms (nvidia_ml_py), or the
+    nvidia-smi query of B200_PROFILING.md when NVML cannot be loaded."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _run_nvml(self):
+        n = self.nvml
+        bits = [(n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (n.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (n.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop_flag:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append([str(mhz), str(self.max_mhz), "0"] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _run(self):
+        if self.nvml is not None:
+            return self._run_nvml()
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
@@ -127,14 +156,13 @@ class ClockSampler:
             self.thread.join(timeout=6)
         sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
-            for k, name in enumerate(names):
+            for k, name in enumerate(self.NAMES):
                 if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
                     reasons.add(name)
         mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -255,6 +283,27 @@ def main():
                "d2h_bytes_per_step": n * (fb + 4 + 1 + 4 + 4), "steps": ke,
                "api": "BatchedToybox.step_host -> tbx_step_host (pinned host actions in; obs, reward, done, score, lives out)"}
 
+    # ---- the HBM-bound layout of the same render path (native RGBA frames), same pool and states: supplementary roofline
+    native = None
+    if rank == 0 and args.obs == "gray84":
+        nb = obs_bytes(args.game, "rgba")
+        nn = min(n, (24 << 30) // nb)                      # output buffer of at most 24 GiB
+        if nn == n:
+            big = torch.empty((n, nb), dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                pool.render(out=big, obs="rgba")
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize(dev)
+            ev[0].record(stream)
+            for _ in range(10):
+                pool.render(out=big, obs="rgba")
+            ev[1].record(stream)
+            torch.cuda.synchronize(dev)
+            nms = ev[0].elapsed_time(ev[1]) / 10
+            nbytes = n * (nb + 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game])
+            native = {"kernel": "render_kernel<%s,rgba>" % args.game, "launch_ms": nms, "bytes_per_launch": nbytes,
+                      "achieved": nbytes / (nms * 1e-3) / 1e9, "unit": "GB/s", "frames_per_sec": n / (nms * 1e-3)}
+            del big
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -269,9 +318,24 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = n * (fb + rec_bytes)          # frame written + state record read, per env, per launch
     achieved = alg_bytes / (render_ms * 1e-3) / 1e9
-    roofline = {"kernel": "render_kernel<%s,%s>" % (args.game, args.obs), "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": alg_bytes, "launch_ms": render_ms, "step_kernel_ms": step_ms}
+    kname = ("area_tile_kernel<%s>" if args.obs == "gray84" else "render_kernel<%s," + args.obs + ">") % args.game
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the committed
+    # `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py); null when never captured
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        key = "%s/%s/%d" % (args.game, args.obs, n)
+        if key in tr:
+            traffic = tr[key]["dram_bytes"]
+    except Exception:
+        pass
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": alg_bytes, "launch_ms": render_ms, "step_kernel_ms": step_ms,
+                "note": "a 7 KB gray84 frame costs more instruction issue than DRAM time; the HBM-bound layout is in roofline_native"}
+    if native is not None:
+        native["frac"] = native["achieved"] / peak
+    roofline["native"] = native
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -1,22 +1,15 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu18.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu18.log
-show() { python - "$1" "$2" <<'PY'
-import json,sys
-for l in open(sys.argv[1]):
-    if l.startswith("{"):
-        d=json.loads(l); r=d["roofline"]; print("%s: %.2f M/s render %.3f ms %.0f GB/s frac %.3f step %.3f ms"%(sys.argv[2], d["value"]/1e6, r["launch_ms"], r["achieved"], r["frac"], r["step_kernel_ms"]))
-PY
-}
-for v in "8 3" "8 2" "8 6" "4 3" "4 6"; do
-  set -- $v
-  export TBX_AREA_TILE_H=$1 TBX_AREA_MAX_RUN=$2
-  timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench18_brk_h$1_r$2.log 2>&1; show gpurun_out/bench18_brk_h$1_r$2.log "breakout gray84 h$1 r$2"
-  timeout 300 python bench.py --policy track --presteps 3000 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench18_track_h$1_r$2.log 2>&1; show gpurun_out/bench18_track_h$1_r$2.log "breakout track h$1 r$2"
-  for g in amidar space_invaders; do
-    timeout 300 python bench.py --game $g --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench18_${g}_h$1_r$2.log 2>&1; show gpurun_out/bench18_${g}_h$1_r$2.log "$g gray84 h$1 r$2"
-  done
-done
-unset TBX_AREA_TILE_H TBX_AREA_MAX_RUN
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:area_tile -s 6 -c 1 -o gpurun_out/prof_render_v18_brk_gray84 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_render18.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:area_tile -s 6 -c 1 -o gpurun_out/prof_render_v18_track python bench.py --policy track --presteps 3000 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_render18t.log 2>&1
+B="--steps 4 --warmup 3 --no-cpu-baseline --no-e2e"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches20.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/launches20.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:area_tile -s 6 -c 1 -o gpurun_out/prof_v20_area_brk python bench.py $B > gpurun_out/ncu20a.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:step_kernel -s 6 -c 1 -o gpurun_out/prof_v20_step_brk python bench.py $B > gpurun_out/ncu20b.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:render_kernel -s 6 -c 1 -o gpurun_out/prof_v20_rgba_brk python bench.py --obs rgba $B > gpurun_out/ncu20c.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 6 -c 1 -o gpurun_out/prof_v20_rgb_amidar python bench.py --game amidar --obs rgb $B > gpurun_out/ncu20d.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:area_tile -s 6 -c 1 -o gpurun_out/prof_v20_area_amidar python bench.py --game amidar $B > gpurun_out/ncu20e.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:area_tile -s 6 -c 1 -o gpurun_out/prof_v20_area_si python bench.py --game space_invaders $B > gpurun_out/ncu20f.log 2>&1
+for f in area_brk step_brk rgba_brk rgb_amidar area_amidar area_si; do python tools/ncu_summary.py gpurun_out/prof_v20_$f.ncu-rep > gpurun_out/ncu_v20_$f.txt 2>&1; done
+ls -la gpurun_out
+rm -f gpurun_out/prof_v20_step_brk.ncu-rep gpurun_out/prof_v20_area_si.ncu-rep gpurun_out/prof_v20_area_amidar.ncu-rep
+timeout 600 python bench.py > gpurun_out/bench20_default.log 2>&1; tail -1 gpurun_out/bench20_default.log | cut -c1-300
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench20_reference.log 2>&1

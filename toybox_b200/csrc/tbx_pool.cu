@@ -309,7 +309,8 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
   }
   const int H = Traits<GAME>::H;
   dim3 grid(blocks(a.n, TBX_EPC), ((MODE == TBX_OBS_GRAY_AREA ? a.out_h : H) + a.band_rows - 1) / a.band_rows);
-  int threads = MODE == TBX_OBS_GRAY_AREA ? 128 : 256;
+  /* measured: Breakout's few primitives keep 4 warps busy, the sprite-heavy games use 8 (profiles/r1_native_layouts.md) */
+  int threads = (MODE == TBX_OBS_GRAY_AREA || GAME == TBX_BREAKOUT) ? 128 : 256;
   if (const char *env = getenv("TBX_RENDER_THREADS")) threads = atoi(env); /* tuning: 32, 64, 128 or 256 */
   if (threads != 32 && threads != 64 && threads != 128 && threads != 256) threads = 128;
   static const TbxAreaPlan no_plan = TbxAreaPlan();
@@ -394,8 +395,8 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
     const char *ksel = getenv("TBX_AREA_KERNEL");
     if (tx <= 5 && ty <= 4 && !(ksel && !strcmp(ksel, "cta"))) {
       const int tx_inst = tx <= 3 ? 3 : tx <= 4 ? 4 : 5;
-      /* tiles of 16 x 8 output pixels, runs of at most 3 tiles: the scratch holds the widest / tallest run window */
-      int ths = 3, max_run = 3;
+      /* tiles of 16 x 8 output pixels, runs of at most 2 tiles: the scratch holds the widest / tallest run window */
+      int ths = 3, max_run = 2;
       if (const char *env = getenv("TBX_AREA_TILE_H")) ths = atoi(env) == 4 ? 2 : 3;
       if (const char *env = getenv("TBX_AREA_MAX_RUN")) max_run = atoi(env);
       if (max_run < 1) max_run = 1;

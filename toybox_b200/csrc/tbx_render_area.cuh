@@ -68,7 +68,7 @@ __device__ __forceinline__ void paint_tile(uint8_t *tile, int stride, int wx0, i
  *   x: x | y << 16;  y: w | h << 16;  z: gray | group << 8 | flags << 16;  w: sprite off | bw << 16 | scale << 24
  *   extent: dxlo | dxhi << 8 | dylo << 16 | dyhi << 24 = the output columns / rows the (clipped) primitive feeds.
  * flags: ENTRY_PAR = member of a PARALLEL draw-list group (no two members conflict, any paint order is right);
- *        ENTRY_SMALL = solid rectangle of at most 256 pixels (one lane paints it alone). */
+ *        ENTRY_SMALL = solid rectangle of at most 128 pixels (one lane can paint it alone). */
 #define TBX_ENTRY_PAR 1u
 #define TBX_ENTRY_SMALL 2u
 template <int W>
@@ -79,7 +79,7 @@ __device__ __forceinline__ bool make_entry(const TbxPrim &p, int g, int gmode, i
   const int dylo = max((int)__ldg(&plan->ydlo[c.y0]), dyA), dyhi = min((int)__ldg(&plan->ydhi[c.y1 - 1]), dyB - 1);
   if (dylo > dyhi) return false;
   const int dxlo = __ldg(&plan->xdlo[c.x0]), dxhi = __ldg(&plan->xdhi[c.x1 - 1]);
-  const uint32_t flags = ((gmode & TBX_GROUP_SERIAL) ? 0u : TBX_ENTRY_PAR) | ((p.bw == 0 && (int)p.w * (int)p.h <= 256) ? TBX_ENTRY_SMALL : 0u);
+  const uint32_t flags = ((gmode & TBX_GROUP_SERIAL) ? 0u : TBX_ENTRY_PAR) | ((p.bw == 0 && (int)p.w * (int)p.h <= 128) ? TBX_ENTRY_SMALL : 0u);
   e.x = (uint32_t)(uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16);
   e.y = (uint32_t)(uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
   e.z = tbx_luma(p.color) | ((uint32_t)g << 8) | (flags << 16);
@@ -348,8 +348,10 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
               /* every hit entry of the same conflict-free group: the small solid ones lane-parallel, the rest one by one */
               const bool mine = ((m >> lane) & 1u) && ((e.z >> 8) & 255u) == ((zl >> 8) & 255u);
               const uint32_t same = __ballot_sync(0xffffffffu, mine);
-              const bool small = mine && ((e.z >> 16) & TBX_ENTRY_SMALL);
-              uint32_t big = same & ~__ballot_sync(0xffffffffu, small);
+              bool small = mine && ((e.z >> 16) & TBX_ENTRY_SMALL);
+              uint32_t smalls = __ballot_sync(0xffffffffu, small);
+              if (__popc(smalls) < 3) { smalls = 0; small = false; } /* too few to pay for one-lane loops: the warp paints each */
+              uint32_t big = same & ~smalls;
               if (small)
                 paint_tile_lane(tile, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
                                 (int16_t)(e.y >> 16), e.z & 255u);
