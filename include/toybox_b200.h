@@ -126,6 +126,29 @@ int tbx_fill_actions(tbx_pool *pool, int32_t *actions_dev, uint64_t seed, uint64
  * into the brick wall -- states the uniform random stream almost never reaches. */
 int tbx_fill_actions_policy(tbx_pool *pool, int32_t *actions_dev, int policy, uint64_t t, void *stream);
 
+/* ---- The DeepMind-style wrapper stack of the reference's trainers, fused.
+ * Replaces, per agent step and for every env at once, the Python chain
+ *   make_atari:    MaxAndSkipEnv(NoopResetEnv(env, noop_max=30), skip=4)     baselines/baselines/common/atari_wrappers.py:107-134,186-209,323-333
+ *   wrap_deepmind: FrameStack(ClipRewardEnv(WarpFrame(FireResetEnv(EpisodicLifeEnv(env)))), 4)   :136-184,211-244,246-275,345-360
+ * plus the reset-on-done of the VecEnv worker (vec_env/subproc_vec_env.py:11-15).  One kernel runs the `skip`
+ * transitions of an agent step (and the whole reset sequence of finished envs); one render pass draws the two states
+ * whose pixel-wise max, down-sampled with INTER_AREA to out_w x out_h, is the observation.
+ * Each of episodic_life / fire_reset / clip_rewards is 0 or 1 (the wrap_deepmind switches); noop_max 0 = no
+ * NoopResetEnv.  The no-op count of reset r of env i is 1 + tbx action-stream index(noop_seed, env0 + i, r, noop_max). */
+typedef struct tbx_wrap tbx_wrap;
+int tbx_wrap_create(tbx_pool *pool, int skip, int noop_max, int episodic_life, int fire_reset, int clip_rewards, int stack_k,
+                    int out_w, int out_h, uint64_t noop_seed, uint64_t env0, tbx_wrap **out);
+int tbx_wrap_destroy(tbx_wrap *wrap);
+/* env.step(action) of the wrapped env for every env (actions_dev: int32[N] gym action indices into the legal set), or
+ * env.reset() for every env when actions_dev == NULL.  obs_ring_dev: uint8[N][stack_k][out_h][out_w], a ring of the
+ * last stack_k observations per env; the newest frame goes to slot *slot_out (host int), older frames follow
+ * backwards modulo stack_k (FrameStack order = slots slot+1, ..., slot+stack_k, modulo stack_k).  Envs whose
+ * observation comes from a reset get it in every slot (FrameStack.reset).  reward: sum over the skipped frames,
+ * its sign when clip_rewards; done: as the agent sees it (game over, or a lost life when episodic_life);
+ * real_done: game over; score / lives: before any reset.  Output pointers may be NULL. */
+int tbx_wrap_step(tbx_wrap *wrap, const int32_t *actions_dev, uint8_t *obs_ring_dev, int32_t *reward_dev, uint8_t *done_dev,
+                  uint8_t *real_done_dev, int32_t *score_dev, int32_t *lives_dev, int *slot_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,9 @@ def lib():
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
         "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
+        "tbx_wrap_create": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, u64, u64, C.POINTER(vp)]),
+        "tbx_wrap_destroy": (i32, [vp]),
+        "tbx_wrap_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)          # AttributeError here = the header and the library disagree
@@ -90,7 +93,8 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_n_envs", "tbx_device", "tbx_legal_actions", "tbx_obs_bytes", "tbx_seed", "tbx_new_game", "tbx_step",
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
-           "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy"]
+           "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy",
+           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step"]
 
 
 def check(rc):

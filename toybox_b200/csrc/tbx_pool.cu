@@ -1,6 +1,7 @@
 /* tbx_pool.cu -- the C ABI of include/toybox_b200.h: pool life cycle, launches, JSON import/export. */
 #include "../../include/toybox_b200.h"
 #include "tbx_kernels.cuh"
+#include "tbx_wrap.cuh"
 #include <map>
 #include <new>
 #include <string>
@@ -359,7 +360,14 @@ template <int GAME> static int launch_render_mode(int mode, int tx, int ty, cons
 
 extern "C" {
 
-int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream) {
+struct DualRender { const uint32_t *planes2; const uint8_t *reset_flags; int stack_k, stack_slot; };
+static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream, const DualRender *dual);
+
+int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream) { return render_impl(p, dst, mode, out_w, out_h, stream, 0); }
+
+} /* extern "C" */
+
+static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream, const DualRender *dual) {
   if (!p || !dst) return set_err(TBX_EINVAL, "pool/dst is NULL");
   if (((uintptr_t)dst & 15) != 0) return set_err(TBX_EINVAL, "dst must be 16-byte aligned");
   size_t fb = tbx_obs_bytes(p, mode, out_w, out_h);
@@ -371,12 +379,14 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   const int pix = mode == TBX_OBS_RGBA ? 4 : mode == TBX_OBS_RGB ? 3 : 1; /* canvas bytes per pixel */
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
+  a.planes2 = dual ? dual->planes2 : 0; a.reset_flags = dual ? dual->reset_flags : 0;
+  a.stack_k = dual ? dual->stack_k : 1; a.stack_slot = dual ? dual->stack_slot : 0; a.env_stride = fb * (size_t)a.stack_k; a.tile_bytes = 0;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h; a.tile_stride = 0; a.warp_bytes = 0; a.list_cap = 0; a.tile_hshift = 0; a.max_run = 0; a.band_rows = 0; a.smem_rects = 0;
   for (int b = 0; b < 2; b++) {
     a.base[b] = pix == 4 ? p->d_base_rgba[b] : pix == 3 ? p->d_base_rgb[b] : p->d_base_gray[b];
     a.base_out[b] = 0; /* INTER_AREA: set below */
   }
-  a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4);
+  a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4) * (dual ? 2 : 1);
   int smem_total, tx = 1, ty = 1;
   const TbxAreaPlan *host_plan = 0;
   if (mode == TBX_OBS_GRAY_AREA) {
@@ -422,7 +432,8 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
         a.list_cap = TBX_TILE_LCAP;
         if (const char *env = getenv("TBX_AREA_LCAP")) a.list_cap = atoi(env); /* tests: small lists force the sweep / per-tile paths */
         if (a.list_cap < 1 || a.list_cap > TBX_TILE_LCAP) a.list_cap = TBX_TILE_LCAP;
-        a.warp_bytes = align16(TBX_TILE_LCAP * 20 + 32 + stride * rows);
+        a.tile_bytes = align16(stride * rows);
+        a.warp_bytes = TBX_TILE_LCAP * 20 + 32 + a.tile_bytes * (dual ? 2 : 1);
         const int smem = a.smem_canvas + (threads / 32) * a.warp_bytes;
         cudaStream_t s = (cudaStream_t)stream;
         if (p->game == TBX_BREAKOUT) return launch_area_tile_taps<TBX_BREAKOUT>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
@@ -430,6 +441,7 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
         return launch_area_tile_taps<TBX_SPACE_INVADERS>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
       }
     }
+    if (dual) return set_err(TBX_EINVAL, "wrapped observations need an output size the tile kernel supports (at most 5 x 4 taps)");
     int nb = p->game == TBX_AMIDAR ? 1 : 2;
     if (const char *env = getenv("TBX_AREA_BANDS")) nb = atoi(env);
     if (nb < 1) nb = 1;
@@ -456,6 +468,87 @@ int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *
   if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
   if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
   return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
+}
+
+/* ---- the fused wrapper stack (tbx_wrap.cuh) */
+struct tbx_wrap {
+  tbx_pool *pool;
+  int skip, noop_max, episodic_life, fire_reset, clip_rewards, stack_k, out_w, out_h;
+  uint64_t noop_seed, env0;
+  uint32_t *planes_prev, *wstate;
+  uint8_t *was_reset;
+  int head; /* ring slot of the newest frame */
+};
+
+extern "C" {
+
+int tbx_wrap_create(tbx_pool *p, int skip, int noop_max, int episodic_life, int fire_reset, int clip_rewards, int stack_k, int out_w, int out_h,
+                    uint64_t noop_seed, uint64_t env0, tbx_wrap **out) {
+  if (!p || !out) return set_err(TBX_EINVAL, "pool/out is NULL");
+  *out = 0;
+  if (skip < 1 || skip > 64 || noop_max < 0 || noop_max > 1000 || stack_k < 1 || stack_k > 16) return set_err(TBX_EINVAL, "skip / noop_max / stack_k out of range");
+  if (tbx_obs_bytes(p, TBX_OBS_GRAY_AREA, out_w, out_h) == 0) return set_err(TBX_EINVAL, "unsupported observation size");
+  CK(cudaSetDevice(p->device));
+  tbx_wrap *w = new (std::nothrow) tbx_wrap();
+  if (!w) return set_err(TBX_ENOMEM, "out of memory");
+  w->pool = p; w->skip = skip; w->noop_max = noop_max; w->episodic_life = episodic_life; w->fire_reset = fire_reset; w->clip_rewards = clip_rewards;
+  w->stack_k = stack_k; w->out_w = out_w; w->out_h = out_h; w->noop_seed = noop_seed; w->env0 = env0; w->head = 0;
+  w->planes_prev = 0; w->wstate = 0; w->was_reset = 0;
+  const size_t plane_bytes = (size_t)p->info->rec_words * p->n_pad * 4;
+  cudaError_t e = cudaMalloc(&w->planes_prev, plane_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&w->wstate, 3 * (size_t)p->n_pad * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&w->was_reset, (size_t)p->n_pad);
+  if (e == cudaSuccess) e = cudaMemcpy(w->planes_prev, p->planes, plane_bytes, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemset(w->wstate, 0, 3 * (size_t)p->n_pad * 4);
+  if (e == cudaSuccess) { /* EpisodicLifeEnv.__init__: lives = 0, was_real_done = True (atari_wrappers.py:155-156) */
+    std::vector<uint32_t> ones((size_t)p->n_pad, 1u);
+    e = cudaMemcpy(w->wstate + p->n_pad, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMemset(w->was_reset, 0, (size_t)p->n_pad);
+  if (e != cudaSuccess) {
+    cudaFree(w->planes_prev); cudaFree(w->wstate); cudaFree(w->was_reset);
+    delete w;
+    return set_err(TBX_ECUDA, std::string("tbx_wrap_create: ") + cudaGetErrorString(e));
+  }
+  *out = w;
+  return TBX_OK;
+}
+
+int tbx_wrap_destroy(tbx_wrap *w) {
+  if (!w) return TBX_OK;
+  cudaSetDevice(w->pool->device);
+  cudaDeviceSynchronize();
+  cudaFree(w->planes_prev); cudaFree(w->wstate); cudaFree(w->was_reset);
+  delete w;
+  return TBX_OK;
+}
+
+int tbx_wrap_step(tbx_wrap *w, const int32_t *actions, uint8_t *obs_ring, int32_t *reward, uint8_t *done, uint8_t *real_done, int32_t *score,
+                  int32_t *lives, int *slot_out, void *stream) {
+  if (!w) return set_err(TBX_EINVAL, "wrap is NULL");
+  tbx_pool *p = w->pool;
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  WrapArgs a;
+  a.planes = p->planes; a.planes_prev = w->planes_prev; a.wstate = w->wstate; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
+  a.legal = p->d_legal; a.n_legal = p->info->n_legal; a.actions = actions;
+  a.skip = w->skip; a.noop_max = w->noop_max; a.episodic_life = w->episodic_life; a.fire_reset = w->fire_reset; a.clip_rewards = w->clip_rewards;
+  a.noop_seed = w->noop_seed; a.env0 = w->env0;
+  a.reward = reward; a.score = score; a.lives = lives; a.done = done; a.real_done = real_done; a.was_reset = w->was_reset;
+  a.stats = p->d_stats; a.bad_actions = p->d_bad;
+  if (p->game == TBX_BREAKOUT) wrap_step_kernel<TBX_BREAKOUT><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  else if (p->game == TBX_AMIDAR) wrap_step_kernel<TBX_AMIDAR><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  else wrap_step_kernel<TBX_SPACE_INVADERS><<<blocks(p->n, 128), 128, 0, s>>>(a);
+  CK(cudaGetLastError());
+  if (obs_ring) {
+    w->head = (w->head + 1) % w->stack_k;
+    DualRender d;
+    d.planes2 = w->planes_prev; d.reset_flags = w->was_reset; d.stack_k = w->stack_k; d.stack_slot = w->head;
+    int r = render_impl(p, obs_ring, TBX_OBS_GRAY_AREA, w->out_w, w->out_h, stream, &d);
+    if (r) return r;
+  }
+  if (slot_out) *slot_out = w->head;
+  return TBX_OK;
 }
 
 int tbx_read_scalars(tbx_pool *p, int32_t *score, int32_t *lives, int32_t *level, void *stream) {

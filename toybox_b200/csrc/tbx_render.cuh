@@ -83,6 +83,12 @@ struct RenderArgs {
   int band_rows;              /* per CTA (blockIdx.y selects the band): canvas rows (native layouts) / output rows (INTER_AREA) */
   int out_h;                  /* INTER_AREA: output rows (host-side launch geometry) */
   int smem_canvas, smem_rects; /* byte offsets into dynamic shared memory */
+  /* dual mode (tbx_wrap.cuh): observation = INTER_AREA(max(frame(planes), frame(planes2))), written into slot
+   * `stack_slot` of a ring of `stack_k` frames per env; envs flagged in reset_flags get the frame in every slot */
+  const uint32_t *planes2;
+  const uint8_t *reset_flags;
+  size_t env_stride; /* bytes between the observations of consecutive envs (frame_bytes * stack_k) */
+  int stack_k, stack_slot, tile_bytes;
   int tile_stride, warp_bytes, list_cap, tile_hshift, max_run; /* INTER_AREA tile kernel (tbx_render_area.cuh): scratch row pitch, shared memory per warp */
 };
 

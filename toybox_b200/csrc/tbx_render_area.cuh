@@ -73,7 +73,7 @@ __device__ __forceinline__ void paint_tile(uint8_t *tile, int stride, int wx0, i
 #define TBX_ENTRY_SMALL 2u
 template <int W>
 __device__ __forceinline__ bool make_entry(const TbxPrim &p, int g, int gmode, int rA, int rB, int dyA, int dyB, const TbxAreaPlan *__restrict__ plan,
-                                           uint4 &e, uint32_t &ext) {
+                                           uint4 &e, uint32_t &ext) { /* g: group index | 0x80 for the second state of dual mode */
   Clip c;
   if (!clip_prim<W>(p, rA, rB, c)) return false;
   const int dylo = max((int)__ldg(&plan->ydlo[c.y0]), dyA), dyhi = min((int)__ldg(&plan->ydhi[c.y1 - 1]), dyB - 1);
@@ -154,6 +154,18 @@ __device__ __forceinline__ void tile_resolve(const uint8_t *tile, int stride, in
   }
 }
 
+/* dual mode: scratch <- max(scratch, scratch2) over the window, four pixels per operation */
+__device__ __forceinline__ void tile_max(uint8_t *tile, const uint8_t *tile2, int stride, int wbytes, int nrows, int lane) {
+  const int nwr = wbytes >> 2;
+  const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
+  const int rstep = 32 >> lg;
+  for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32)
+    for (int y = lane >> lg; y < nrows; y += rstep) {
+      uint32_t *p = reinterpret_cast<uint32_t *>(tile + y * stride) + cc;
+      *p = __vmaxu4(*p, *(reinterpret_cast<const uint32_t *>(tile2 + y * stride) + cc));
+    }
+}
+
 __device__ __forceinline__ void paint_entry_coop(uint8_t *tile, int stride, int wx0, int wy0, int wx1, int wy1, const uint4 &q, const uint32_t *R, int lane) {
   paint_tile(tile, stride, wx0, wy0, wx1, wy1, (int16_t)(q.x & 0xffffu), (int16_t)(q.x >> 16), (int16_t)(q.y & 0xffffu), (int16_t)(q.y >> 16),
              q.z & 255u, q.w, R, lane);
@@ -162,8 +174,9 @@ __device__ __forceinline__ void paint_entry_coop(uint8_t *tile, int stride, int 
 /* One tile row with more entries than the list holds: every tile of the row re-builds the primitives and paints
  * those that touch it, strictly in draw order (slow, but always correct). */
 template <int GAME, int TX, int TY>
-__device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables, int base,
-                                              const uint8_t *bfr, const TbxAreaPlan *__restrict__ plan, const TbxAreaPlan &cp, uint8_t *tile, int stride,
+__device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const uint32_t *R2, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
+                                              int base, int base2, const uint8_t *bfr, const uint8_t *bfr2, const TbxAreaPlan *__restrict__ plan, const TbxAreaPlan &cp,
+                                              uint8_t *tile, uint8_t *tile2, int stride,
                                               int ty, int ths, int rA, int rB, int dyA, int dyB, uint8_t *out, int lane) {
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H;
@@ -173,31 +186,37 @@ __device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const typename 
   for (int dxA = 0; dxA < dw; dxA += 16) {
     const int dxL = min(dxA + 15, dw - 1);
     const int wx0 = cp.xs0[dxA] & ~3, wx1 = min(W, ((int)cp.xs0[dxL] + TX + 3) & ~3);
-    tile_load<W>(tile, stride, bfr, wx0, wy0, wx1, wy1, lane);
-    __syncwarp();
-    for (int g = 0; g < T::NG; g++) {
-      int gb, ge, gmode;
-      T::group(g, R, tables, base, gb, ge, gmode);
-      for (int s0 = gb; s0 < ge; s0 += 32) {
-        const int s = s0 + lane;
-        TbxPrim p = tbx_prim_none();
-        if (s < ge) p = T::prim(R, cfg, tables, s, base);
-        uint4 e;
-        uint32_t ext;
-        bool hit = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
-        hit = hit && (int)(ext & 255u) <= dxL && (int)((ext >> 8) & 255u) >= dxA;
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          uint4 q;
-          q.x = __shfl_sync(0xffffffffu, e.x, l); q.y = __shfl_sync(0xffffffffu, e.y, l);
-          q.z = __shfl_sync(0xffffffffu, e.z, l); q.w = __shfl_sync(0xffffffffu, e.w, l);
-          paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
-          __syncwarp();
+    for (int st = 0; st < (R2 ? 2 : 1); st++) {
+      const uint32_t *Rs = st ? R2 : R;
+      const int bs = st ? base2 : base;
+      uint8_t *ts = st ? tile2 : tile;
+      tile_load<W>(ts, stride, st ? bfr2 : bfr, wx0, wy0, wx1, wy1, lane);
+      __syncwarp();
+      for (int g = 0; g < T::NG; g++) {
+        int gb, ge, gmode;
+        T::group(g, Rs, tables, bs, gb, ge, gmode);
+        for (int s0 = gb; s0 < ge; s0 += 32) {
+          const int s = s0 + lane;
+          TbxPrim p = tbx_prim_none();
+          if (s < ge) p = T::prim(Rs, cfg, tables, s, bs);
+          uint4 e;
+          uint32_t ext;
+          bool hit = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
+          hit = hit && (int)(ext & 255u) <= dxL && (int)((ext >> 8) & 255u) >= dxA;
+          unsigned m = __ballot_sync(0xffffffffu, hit);
+          while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            uint4 q;
+            q.x = __shfl_sync(0xffffffffu, e.x, l); q.y = __shfl_sync(0xffffffffu, e.y, l);
+            q.z = __shfl_sync(0xffffffffu, e.z, l); q.w = __shfl_sync(0xffffffffu, e.w, l);
+            paint_entry_coop(ts, stride, wx0, wy0, wx1, wy1, q, Rs, lane);
+            __syncwarp();
+          }
         }
       }
     }
+    if (R2) { tile_max(tile, tile2, stride, wx1 - wx0, wy1 - wy0, lane); __syncwarp(); }
     tile_resolve<TX, TY>(tile, stride, wx0, wy0, dxA, dxL, dy0, dy1, dw, plan, out, lane);
     __syncwarp();
   }
@@ -218,9 +237,14 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
   const int ne = min(TBX_EPC, a.n - e0);
+  const bool dual = a.planes2 != 0; /* observation = down-sample of max(frame of planes, frame of planes2) */
+  uint32_t *recs2 = recs + RW * TBX_EPC;
   for (int i = tid; i < RW * TBX_EPC; i += blockDim.x) {
     const int w = i / TBX_EPC, j = i - w * TBX_EPC;
-    if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
+    if (j < ne) {
+      recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
+      if (dual) recs2[j * RW + w] = a.planes2[(size_t)w * a.n_pad + e0 + j];
+    }
   }
   __syncthreads(); /* the only CTA barrier: from here on every warp works alone */
 
@@ -229,6 +253,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
   uint32_t *exts = reinterpret_cast<uint32_t *>(wmem + TBX_TILE_LCAP * 16);
   uint32_t *tmask = exts + TBX_TILE_LCAP;
   uint8_t *tile = reinterpret_cast<uint8_t *>(tmask + 8);
+  uint8_t *tile2 = tile + a.tile_bytes; /* dual mode: the second state's window */
   const int stride = a.tile_stride;
   const int ths = a.tile_hshift; /* tiles are 16 x (1 << ths) output pixels */
   const int dw = cp.dw, dh = cp.dh, nty = (dh + (1 << ths) - 1) >> ths;
@@ -238,7 +263,11 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
     const uint32_t *R = recs + j * RW;
     const int base = T::base_id(R, cfg, tables);
     const uint8_t *bfr = base ? a.base[1] : a.base[0];
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    const uint32_t *R2 = dual ? recs2 + j * RW : 0;
+    const int base2 = dual ? T::base_id(R2, cfg, tables) : base;
+    const uint8_t *bfr2 = base2 ? a.base[1] : a.base[0];
+    const bool redo_all = base2 != base; /* the two frames differ everywhere the base frames do: recompute every tile */
+    uint8_t *out = a.dst + (size_t)(e0 + j) * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
     { /* 1. the static part of the frame */
       const uint8_t *src = base ? a.base_out[1] : a.base_out[0];
       const int nb = dw * dh;
@@ -265,26 +294,30 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       __syncwarp();
       int n = 0;
       bool overflow = false;
-      for (int g = 0; g < T::NG && !overflow; g++) {
-        int gb, ge, gmode;
-        T::group(g, R, tables, base, gb, ge, gmode);
-        for (int s0 = gb; s0 < ge; s0 += 32) {
-          const int s = s0 + lane;
-          TbxPrim p = tbx_prim_none();
-          if (s < ge) p = T::prim(R, cfg, tables, s, base);
-          uint4 e;
-          uint32_t ext;
-          const bool ok = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (m == 0) continue;
-          if (n + __popc(m) > a.list_cap) { overflow = true; break; }
-          if (ok) {
-            const int slot = n + __popc(m & lt_mask);
-            list[slot] = e;
-            exts[slot] = ext;
-            mark_tiles(tmask, ext, ths);
+      for (int st = 0; st < (dual ? 2 : 1) && !overflow; st++) {
+        const uint32_t *Rs = st ? R2 : R;
+        const int bs = st ? base2 : base;
+        for (int g = 0; g < T::NG && !overflow; g++) {
+          int gb, ge, gmode;
+          T::group(g, Rs, tables, bs, gb, ge, gmode);
+          for (int s0 = gb; s0 < ge; s0 += 32) {
+            const int s = s0 + lane;
+            TbxPrim p = tbx_prim_none();
+            if (s < ge) p = T::prim(Rs, cfg, tables, s, bs);
+            uint4 e;
+            uint32_t ext;
+            const bool ok = make_entry<W>(p, g | (st << 7), gmode, rA, rB, dyA, dyB, plan, e, ext);
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m == 0) continue;
+            if (n + __popc(m) > a.list_cap) { overflow = true; break; }
+            if (ok) {
+              const int slot = n + __popc(m & lt_mask);
+              list[slot] = e;
+              exts[slot] = ext;
+              mark_tiles(tmask, ext, ths);
+            }
+            n += __popc(m);
           }
-          n += __popc(m);
         }
       }
       if (overflow && nsw < nty) { /* halve the sweeps' height and start over (finished tiles are simply redone) */
@@ -295,10 +328,19 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       __syncwarp();
 
       if (overflow) {
-        tile_row_rebuild<GAME, TX, TY>(R, cfg, tables, base, bfr, plan, cp, tile, stride, tyA, ths, rA, rB, dyA, dyB, out, lane);
+        tile_row_rebuild<GAME, TX, TY>(R, R2, cfg, tables, base, base2, bfr, bfr2, plan, cp, tile, tile2, stride, tyA, ths, rA, rB, dyA, dyB, out, lane);
         continue;
       }
-      if (n == 0) continue;
+      if (redo_all) { /* every tile of the sweep, whether an entry touches it or not */
+        __syncwarp();
+        const uint32_t allcols = (1u << ((dw + 15) >> 4)) - 1u;
+        if (lane < 8) {
+          uint32_t mw = 0;
+          for (int k = 0; k < 4; k++) { const int ty = lane * 4 + k; if (ty >= tyA && ty < tyB) mw |= allcols << (k * 8); }
+          tmask[lane] = mw;
+        }
+        __syncwarp();
+      } else if (n == 0) continue;
 
       /* 3. the marked tiles, one RUN of horizontally adjacent marked tiles of a tile row at a time.  Lanes hold the
        * extents of the entries (32 per chunk, one per lane), so "which entries feed this run, and which of its pixels" is one
@@ -322,12 +364,14 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
             hm[c] = __ballot_sync(0xffffffffu, hit);
             if (hit) { bx0 = min(bx0, xlo); bx1 = max(bx1, xhi); by0 = min(by0, ylo); by1 = max(by1, yhi); }
           }
-          const int dx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)), dx1 = min(rx1, __reduce_max_sync(0xffffffffu, bx1));
-          const int dy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), dy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
+          int dx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)), dx1 = min(rx1, __reduce_max_sync(0xffffffffu, bx1));
+          int dy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), dy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
+          if (redo_all) { dx0 = rx0; dx1 = min(rx1, dw - 1); dy0 = ry0; dy1 = min(ry1, dh - 1); }
           if (dx0 > dx1 || dy0 > dy1) continue;
           const int wx0 = cp.xs0[dx0] & ~3, wx1 = min(W, ((int)cp.xs0[dx1] + TX + 3) & ~3);
           const int wy0 = cp.ys0[dy0], wy1 = min(H, (int)cp.ys0[dy1] + TY);
           tile_load<W>(tile, stride, bfr, wx0, wy0, wx1, wy1, lane);
+          if (dual) tile_load<W>(tile2, stride, bfr2, wx0, wy0, wx1, wy1, lane);
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
@@ -338,9 +382,12 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
             while (m) {
               const int l = __ffs(m) - 1;
               const uint32_t zl = __shfl_sync(0xffffffffu, e.z, l);
+              const bool st2 = (zl >> 15) & 1u; /* entry of the second state: its own scratch and record */
+              uint8_t *ts = st2 ? tile2 : tile;
+              const uint32_t *Rs = st2 ? R2 : R;
               if (!((zl >> 16) & TBX_ENTRY_PAR)) { /* in-order group: one entry at a time */
                 const uint4 q = list[c * 32 + l];
-                paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
+                paint_entry_coop(ts, stride, wx0, wy0, wx1, wy1, q, Rs, lane);
                 __syncwarp();
                 m &= m - 1;
                 continue;
@@ -353,21 +400,37 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
               if (__popc(smalls) < 3) { smalls = 0; small = false; } /* too few to pay for one-lane loops: the warp paints each */
               uint32_t big = same & ~smalls;
               if (small)
-                paint_tile_lane(tile, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
+                paint_tile_lane(ts, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
                                 (int16_t)(e.y >> 16), e.z & 255u);
               __syncwarp();
               while (big) {
                 const int lb = __ffs(big) - 1;
                 big &= big - 1;
                 const uint4 q = list[c * 32 + lb];
-                paint_entry_coop(tile, stride, wx0, wy0, wx1, wy1, q, R, lane);
+                paint_entry_coop(ts, stride, wx0, wy0, wx1, wy1, q, Rs, lane);
                 __syncwarp();
               }
               m &= ~same;
             }
           }
+          if (dual) { tile_max(tile, tile2, stride, wx1 - wx0, wy1 - wy0, lane); __syncwarp(); }
           tile_resolve<TX, TY>(tile, stride, wx0, wy0, dx0, dx1, dy0, dy1, dw, plan, out, lane);
           __syncwarp(); /* the scratch canvas is overwritten by the next run */
+        }
+      }
+    }
+    /* FrameStack.reset (atari_wrappers.py:262-266): a reset observation fills every slot of the env's ring */
+    if (a.reset_flags && a.stack_k > 1 && a.reset_flags[e0 + j]) {
+      __syncwarp();
+      uint8_t *ring = a.dst + (size_t)(e0 + j) * a.env_stride;
+      const int nb = dw * dh;
+      for (int k = 0; k < a.stack_k; k++) {
+        if (k == a.stack_slot) continue;
+        uint8_t *o2 = ring + (size_t)k * a.frame_bytes;
+        if ((a.frame_bytes & 15) == 0) {
+          for (int i = lane; i < (nb >> 4); i += 32) reinterpret_cast<uint4 *>(o2)[i] = __ldcg(reinterpret_cast<const uint4 *>(out) + i);
+        } else {
+          for (int i = lane; i < nb; i += 32) o2[i] = __ldcg(out + i);
         }
       }
     }
