@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--policy", default="random", choices=["random", "track"],
                     help="random = the headline uniform stream; track = scripted Breakout ball tracking (breaks bricks)")
     ap.add_argument("--presteps", type=int, default=0, help="untimed step-only frames before the warm-up")
+    ap.add_argument("--wrapped", action="store_true",
+                    help="supplementary line: the fused DeepMind wrapper stack (frame skip 4, max of 2 frames, 84x84, FrameStack 4)")
     return ap.parse_args()
 
 
@@ -166,10 +168,52 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def wrapped_arm(args):
+    """Supplementary measurement: agent steps of the fused wrapper stack; 1 agent step = 4 game frames."""
+    import numpy as np
+    import torch
+    import toybox_b200
+    from toybox_b200.wrappers import DeepmindToybox
+    toybox_b200.lib()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    n = args.envs
+    env = DeepmindToybox(args.game, n, device=dev, seeds=(1234 + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF)
+    env.reset()
+    acts = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(ACTION_SEED)
+    pool_acts = torch.randint(0, env.n_actions, (64, n), device=dev, dtype=torch.int32, generator=gen)
+    for t in range(max(args.warmup, 3)):
+        env.step(pool_acts[t % 64])
+    torch.cuda.synchronize(dev)
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(K):
+        env.step(pool_acts[t % 64])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    env.check()
+    line = {"metric": "agent-steps/sec through the fused wrapper stack", "value": n * K / (ms * 1e-3), "unit": "agent-steps/s",
+            "game_frames_per_sec": 4 * n * K / (ms * 1e-3), "n_gpus": 1, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms / K,
+            "higher_is_better": True, "supplementary": True, "dtype": GAME_DTYPE[args.game], "data": "synthetic",
+            "config": {"workload": "%s %d envs, frame skip 4 + max of 2 frames + 84x84 INTER_AREA + FrameStack 4 ring, uniform random actions" % (args.game, n)},
+            "gpu_launches": 2 * K, "launches_per_step": ["wrap_step_kernel", "area_tile_kernel (dual)"],
+            "episode_stats": env.pool.episode_stats()}
+    print(json.dumps(line), flush=True)
+    env.close()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.wrapped:
+        wrapped_arm(args)
         return
     import numpy as np
     import torch
