@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 GAMES = ["breakout", "amidar", "space_invaders"]
 VARIANTS = [{}, {"TBX_AREA_LCAP": "24"}, {"TBX_AREA_LCAP": "3"}, {"TBX_AREA_KERNEL": "cta"}, {"TBX_AREA_THREADS": "128"},
-            {"TBX_AREA_TILE_H": "4", "TBX_AREA_MAX_RUN": "8"}, {"TBX_AREA_MAX_RUN": "1", "TBX_AREA_LCAP": "40"}]
+            {"TBX_AREA_TILE_H": "4", "TBX_AREA_MAX_RUN": "8"}, {"TBX_AREA_TILE_H": "16"}, {"TBX_AREA_MAX_RUN": "1", "TBX_AREA_LCAP": "40"}]
 SIZES = [(84, 84), (96, 80), (64, 64), (48, 60), (100, 37)]
 
 

@@ -407,7 +407,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
       const int tx_inst = tx <= 3 ? 3 : tx <= 4 ? 4 : 5;
       /* tiles of 16 x 8 output pixels, runs of at most 2 tiles: the scratch holds the widest / tallest run window */
       int ths = 3, max_run = 2;
-      if (const char *env = getenv("TBX_AREA_TILE_H")) ths = atoi(env) == 4 ? 2 : 3;
+      if (const char *env = getenv("TBX_AREA_TILE_H")) ths = atoi(env) == 4 ? 2 : atoi(env) == 16 ? 4 : 3;
       if (const char *env = getenv("TBX_AREA_MAX_RUN")) max_run = atoi(env);
       if (max_run < 1) max_run = 1;
       if (max_run > 8) max_run = 8;

@@ -51,6 +51,7 @@ template <> struct Traits<TBX_BREAKOUT> {
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return brk_prim_delta(R, c, t, s, base); }
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return brk_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int base, int &b, int &e, int &mode) { brk_group(g, R, t, base, b, e, mode); }
+  static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
 };
 template <> struct Traits<TBX_SPACE_INVADERS> {
   typedef SiCfg Cfg; typedef int Table; typedef SiRec Rec;
@@ -60,6 +61,7 @@ template <> struct Traits<TBX_SPACE_INVADERS> {
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &, const Table *, int s, int) { return si_prim(R, s); }
   static __device__ __forceinline__ int base_id(const uint32_t *, const Cfg &, const Table *) { return 0; }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
+  static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
 };
 template <> struct Traits<TBX_AMIDAR> {
   typedef AmiCfg Cfg; typedef AmiTable Table; typedef AmiRec Rec;
@@ -69,6 +71,21 @@ template <> struct Traits<TBX_AMIDAR> {
   static __device__ __forceinline__ TbxPrim prim(const uint32_t *R, const Cfg &c, const Table *t, int s, int base) { return ami_prim_delta(R, c, t, s, base); }
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return ami_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { ami_group(g, b, e, mode); }
+  /* Warp-cooperative narrowing of a group's slot range (every lane of the warp must call it): of the 31 x 32 maze
+   * tiles only the rows whose packed words differ from the config board can differ from base frame 1 -- lane r
+   * compares row r, a ballot gives the first and last such row.  (A superset: equal looks may hide behind unequal
+   * tags; ami_prim_delta still decides per tile.) */
+  static __device__ __forceinline__ void trim(int g, const uint32_t *R, const Cfg &c, int base, int &b, int &e) {
+    if (g != 0 || base != 1) return;
+    const int lane = threadIdx.x & 31;
+    bool diff = false;
+    if (lane < TBX_AMI_BH)
+      diff = ((R[AMI_W(tiles) + 2 * lane] ^ c.board[lane][0]) | (R[AMI_W(tiles) + 2 * lane + 1] ^ c.board[lane][1])) != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, diff);
+    if (m == 0) { e = b; return; }
+    b = AMI_SLOT_TILES + 32 * (__ffs(m) - 1);
+    e = AMI_SLOT_TILES + 32 * (32 - __clz(m));
+  }
 };
 
 struct RenderArgs {
@@ -186,6 +203,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
   for (int g = 0; g < T::NG; g++) {
     int gb, ge, gmode;
     T::group(g, R, tables, base, gb, ge, gmode);
+    T::trim(g, R, cfg, base, gb, ge);
     if (gb >= ge) { prev_nosync = false; continue; } /* empty group (uniform across the CTA); its neighbour's flag does not carry over */
     const bool cur_multi = !(gmode & TBX_GROUP_SERIAL) && (ge - gb) > 32;
     if (have_prev && (prev_multi || cur_multi) && !prev_nosync) __syncthreads();
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
    * per-thread load/store instructions. */
   const int r0 = blockIdx.y * a.band_rows, r1 = min(H, r0 + a.band_rows);
   int canvas_base = -1;
+#pragma unroll 1 /* the body is large: unrolled over the 8 envs it no longer fits the instruction cache (measured: 2x slower) */
   for (int j = 0; j < ne; j++) {
     const uint32_t *R = recs + j * RW;
     const int base = env_base[j];
@@ -462,7 +481,8 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     if (tid == 0) rect_n[(j - 1) & 1] = 0;
     paint_env<GAME, PIX>(R, cfg, tables, base, canvas, r0, r1, rects, n_rects, big_buf, n_big);
     /* every thread makes its canvas writes visible to the async proxy; the canvas may be touched again once the
-     * engine has read it */
+     * engine has read it.  (Half of all stall samples of the sprite-heavy games sit in this wait; two half-height
+     * canvases painted alternately were measured and are slower -- the per-band fixed work doubles.) */
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {

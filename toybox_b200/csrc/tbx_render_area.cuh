@@ -195,6 +195,7 @@ __device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const uint32_t 
       for (int g = 0; g < T::NG; g++) {
         int gb, ge, gmode;
         T::group(g, Rs, tables, bs, gb, ge, gmode);
+          T::trim(g, Rs, cfg, bs, gb, ge);
         for (int s0 = gb; s0 < ge; s0 += 32) {
           const int s = s0 + lane;
           TbxPrim p = tbx_prim_none();
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
         for (int g = 0; g < T::NG && !overflow; g++) {
           int gb, ge, gmode;
           T::group(g, Rs, tables, bs, gb, ge, gmode);
+          T::trim(g, Rs, cfg, bs, gb, ge);
           for (int s0 = gb; s0 < ge; s0 += 32) {
             const int s = s0 + lane;
             TbxPrim p = tbx_prim_none();
