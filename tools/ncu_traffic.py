@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Record the DRAM traffic of one profiled launch (an `ncu --set full` .ncu-rep) in profiles/r1_traffic.json, the file
-bench.py reads `roofline.traffic` from.  usage: tools/ncu_traffic.py rep.ncu-rep game/obs/n_envs"""
+bench.py reads `roofline.traffic` from.  usage: tools/ncu_traffic.py rep.ncu-rep game/obs/n_envs [out.json]"""
 import csv
 import json
 import os
@@ -22,7 +22,7 @@ def main():
         return float(row[i]) * scale
 
     rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "r1_traffic.json")
     tr = json.load(open(path)) if os.path.exists(path) else {}
     tr[key] = {"kernel": row[hdr.index("Kernel Name")], "dram_bytes": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
                "source": os.path.basename(rep)}
