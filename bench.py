@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--policy", default="random", choices=["random", "track"],
                     help="random = the headline uniform stream; track = scripted Breakout ball tracking (breaks bricks)")
     ap.add_argument("--presteps", type=int, default=0, help="untimed step-only frames before the warm-up")
+    ap.add_argument("--mixed", type=int, default=0, metavar="TOTAL_ENVS",
+                    help="supplementary line: BASELINE configs[4] -- TOTAL_ENVS (e.g. 1048576) split 1/3 per game and evenly over the GPUs, "
+                         "gray84, NCCL all-reduce of the episode statistics every 256 steps")
     ap.add_argument("--wrapped", action="store_true",
                     help="supplementary line: the fused DeepMind wrapper stack (frame skip 4, max of 2 frames, 84x84, FrameStack 4)")
     return ap.parse_args()
@@ -207,10 +210,92 @@ def wrapped_arm(args):
     env.close()
 
 
+def mixed_arm(args):
+    """Supplementary measurement, BASELINE.json configs[4]: the mixed-game sweep.  Every rank owns one pool per game
+    (its shard of that game's env-id range, seeds from the global env id); a step = fill + step + render of all three
+    pools; every 256 steps the per-game episode statistics are all-reduced (NCCL) -- the path's only collective."""
+    import numpy as np
+    import torch
+    import toybox_b200
+    from toybox_b200 import distributed as D
+    toybox_b200.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    games = list(toybox_b200.GAMES)
+    per_game = [args.mixed // 3, args.mixed // 3, args.mixed - 2 * (args.mixed // 3)]
+    pools, bufs = [], []
+    for game, total in zip(games, per_game):
+        env0, n = D.shard(total, rank, world)
+        pool = toybox_b200.BatchedToybox(game, n, device=dev, obs="gray84", seeds=D.global_seeds(1234, env0, n))
+        pools.append((pool, env0, n))
+        bufs.append((torch.empty((n,) + pool.obs_shape, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev)))
+    stream = torch.cuda.current_stream(dev)
+    reduced = [None] * 3
+
+    def step(t):
+        for (pool, env0, n), (obs, acts) in zip(pools, bufs):
+            pool.fill_random_actions(acts, ACTION_SEED, t, env0)
+            pool.apply_ale_action(acts, auto_reset=True)
+            pool.render(out=obs)
+        if t % 256 == 255:
+            for k, (pool, _, _) in enumerate(pools):
+                reduced[k] = D.reduce_episode_stats(pool.episode_stats(), device=dev)
+
+    t = 0
+    for _ in range(max(args.warmup, 3)):
+        step(t)
+        t += 1
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    K = args.steps
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step(t)
+        t += 1
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    for pool, _, _ in pools:
+        pool.check()
+    stats = [D.reduce_episode_stats(pool.episode_stats(), device=dev) for pool, _, _ in pools]
+    if dist is not None:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    if rank == 0:
+        line = {"metric": "env-steps/sec with rendered frames, mixed games", "value": args.mixed * K / (ms * 1e-3), "unit": "env-steps/s",
+                "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "strong", "supplementary": True, "dtype": "f64+i32+u8", "data": "synthetic",
+                "config": {"workload": "mixed-game sweep: %d envs total = %s, split evenly over %d GPU(s), gray84 obs, random legal actions, "
+                                       "auto-reset, NCCL all-reduce of per-game episode statistics every 256 steps"
+                                       % (args.mixed, " + ".join("%d %s" % (n, g) for g, n in zip(games, per_game)), world)},
+                "gpu_launches": 9 * K, "collective": "all_reduce of 3 x [episodes, sum_return, sum_length, max_return] int64 every 256 steps",
+                "episode_stats": {g: s for g, s in zip(games, stats)}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.mixed:
+        mixed_arm(args)
         return
     if args.wrapped:
         wrapped_arm(args)

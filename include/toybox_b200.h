@@ -126,6 +126,19 @@ int tbx_fill_actions(tbx_pool *pool, int32_t *actions_dev, uint64_t seed, uint64
  * into the brick wall -- states the uniform random stream almost never reaches. */
 int tbx_fill_actions_policy(tbx_pool *pool, int32_t *actions_dev, int policy, uint64_t t, void *stream);
 
+/* ---- Vectorised property access: one scalar of the JSON state schema for EVERY env without a JSON round
+ * trip.  Replaces, at batch size N, get_property / set-through-Intervention on one env
+ * (toybox/interventions/core.py:271-304, base.py:387-408) and the per-game helpers built on them
+ * (interventions/breakout.py:303-429, amidar.py:406-481).  `path` uses the schema's names: "lives", "score",
+ * "paddle.position.x", "balls[0].velocity.y", "bricks[17].alive", "ufo.appearance_counter", "enemies[3].alive",
+ * "player.position.x", "jump_timer", "board.boxes[4].painted", ...  kind: 0 int32, 1 float64, 2 bool, 3 bool stored as
+ * one bit, 4 Option<i32> (null <-> INT32_MIN).  Values travel as int32[N] (kinds 0, 2, 3, 4) or float64[N] (kind 1)
+ * device arrays; mask_dev (may be NULL) = uint8[N], only flagged envs are written.  Setting "score" also sets the
+ * env's reward baseline, as tbx_state_from_json does. */
+int tbx_field_lookup(const char *game, const char *path, int *word, int *kind, int *bit);
+int tbx_field_get(tbx_pool *pool, const char *path, void *out_dev, void *stream);
+int tbx_field_set(tbx_pool *pool, const char *path, const void *values_dev, const uint8_t *mask_dev, void *stream);
+
 /* ---- The DeepMind-style wrapper stack of the reference's trainers, fused.
  * Replaces, per agent step and for every env at once, the Python chain
  *   make_atari:    MaxAndSkipEnv(NoopResetEnv(env, noop_max=30), skip=4)     baselines/baselines/common/atari_wrappers.py:107-134,186-209,323-333

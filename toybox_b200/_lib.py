@@ -77,6 +77,9 @@ def lib():
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
         "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
+        "tbx_field_lookup": (i32, [cp, cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "tbx_field_get": (i32, [vp, cp, vp, vp]),
+        "tbx_field_set": (i32, [vp, cp, vp, vp, vp]),
         "tbx_wrap_create": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, u64, u64, C.POINTER(vp)]),
         "tbx_wrap_destroy": (i32, [vp]),
         "tbx_wrap_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]),
@@ -94,7 +97,7 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
            "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy",
-           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step"]
+           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set"]
 
 
 def check(rc):

@@ -107,6 +107,37 @@ __global__ void breakout_tracking_actions_kernel(const uint32_t *planes, int n, 
   }
   actions[env] = a;
 }
+/* One property of the state schema for every env (tbx_fields.h): the plane of its word.  kind: 0 i32, 1 f64, 2 bool,
+ * 3 bit of a mask word, 4 Option<i32> (None <-> TBX_NONE).  out / values: int32[N] (kinds 0, 2, 3, 4) or f64[N] (kind 1);
+ * mask (may be NULL): uint8[N], only flagged envs are written. */
+__global__ void field_get_kernel(const uint32_t *planes, int n, int n_pad, int word, int kind, int bit, int32_t *out_i, double *out_d) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  const uint32_t v = planes[(size_t)word * n_pad + env];
+  if (kind == 1) {
+    const uint64_t u = (uint64_t)v | ((uint64_t)planes[(size_t)(word + 1) * n_pad + env] << 32);
+    out_d[env] = __longlong_as_double((long long)u);
+  } else if (kind == 3) out_i[env] = (int32_t)((v >> bit) & 1u);
+  else if (kind == 2) out_i[env] = v != 0;
+  else out_i[env] = (int32_t)v;
+}
+__global__ void field_set_kernel(uint32_t *planes, int n, int n_pad, int word, int kind, int bit, const int32_t *val_i, const double *val_d,
+                                 const uint8_t *mask, int also_word) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n || (mask && !mask[env])) return;
+  uint32_t *p = planes + (size_t)word * n_pad + env;
+  if (kind == 1) {
+    const uint64_t u = (uint64_t)__double_as_longlong(val_d[env]);
+    p[0] = (uint32_t)u;
+    p[n_pad] = (uint32_t)(u >> 32);
+  } else if (kind == 3) *p = val_i[env] ? (*p | (1u << bit)) : (*p & ~(1u << bit));
+  else if (kind == 2) *p = val_i[env] != 0;
+  else {
+    *p = (uint32_t)val_i[env];
+    if (also_word >= 0) planes[(size_t)also_word * n_pad + env] = (uint32_t)val_i[env]; /* score: prev_score follows, as write_state_json does */
+  }
+}
+
 /* records (AoS, rw words each) <-> planes, for the JSON import/export of a few envs */
 __global__ void gather_kernel(const uint32_t *planes, int n_pad, const int32_t *ids, int k, int rw, uint32_t *recs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -2,6 +2,7 @@
 #include "../../include/toybox_b200.h"
 #include "tbx_kernels.cuh"
 #include "tbx_wrap.cuh"
+#include "tbx_fields.h"
 #include <map>
 #include <new>
 #include <string>
@@ -548,6 +549,45 @@ int tbx_wrap_step(tbx_wrap *w, const int32_t *actions, uint8_t *obs_ring, int32_
     if (r) return r;
   }
   if (slot_out) *slot_out = w->head;
+  return TBX_OK;
+}
+
+int tbx_field_lookup(const char *game, const char *path, int *word, int *kind, int *bit) {
+  int g = tbx::game_from_name(game);
+  if (g < 0 || !path) return set_err(TBX_EINVAL, "unknown game or NULL path");
+  tbxfields::Field f;
+  if (!tbxfields::lookup(g, path, &f)) return set_err(TBX_EINVAL, std::string("no scalar state property '") + path + "' for " + game);
+  if (word) *word = f.word;
+  if (kind) *kind = f.kind;
+  if (bit) *bit = f.bit;
+  return TBX_OK;
+}
+static int field_of(tbx_pool *p, const char *path, tbxfields::Field *f) {
+  if (!p || !path) return set_err(TBX_EINVAL, "pool/path is NULL");
+  if (!tbxfields::lookup(p->game, path, f)) return set_err(TBX_EINVAL, std::string("no scalar state property '") + path + "' for " + p->info->name);
+  return TBX_OK;
+}
+int tbx_field_get(tbx_pool *p, const char *path, void *out, void *stream) {
+  tbxfields::Field f;
+  int r = field_of(p, path, &f);
+  if (r) return r;
+  if (!out) return set_err(TBX_EINVAL, "out is NULL");
+  CK(cudaSetDevice(p->device));
+  field_get_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, f.word, f.kind, f.bit < 0 ? 0 : f.bit,
+                                                                         (int32_t *)out, (double *)out);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+int tbx_field_set(tbx_pool *p, const char *path, const void *values, const uint8_t *mask, void *stream) {
+  tbxfields::Field f;
+  int r = field_of(p, path, &f);
+  if (r) return r;
+  if (!values) return set_err(TBX_EINVAL, "values is NULL");
+  CK(cudaSetDevice(p->device));
+  const int also = (f.kind == TBX_F_I32 && f.word == TBX_FW(TbxHdr, score)) ? TBX_FW(TbxHdr, prev_score) : -1;
+  field_set_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, f.word, f.kind, f.bit < 0 ? 0 : f.bit,
+                                                                         (const int32_t *)values, (const double *)values, mask, also);
+  CK(cudaGetLastError());
   return TBX_OK;
 }
 

@@ -87,3 +87,54 @@ class BatchedIntervention:
         elif changed:
             self.pool.write_state_json([self.states[k] for k in changed], self.env_ids[changed])
         return False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's per-game intervention helpers at batch N, on SoA planes instead of JSON.  `mask`
+# (optional, N booleans) selects the envs an edit applies to.
+
+def breakout_add_channel(pool, col, mask=None):
+    """BreakoutIntervention.add_channel(col) (toybox/interventions/breakout.py:406-410) for every (masked) env: the
+    bricks of column `col` are removed.  Bricks are column-major (test/interventions/test_get_property.py:41-44)."""
+    _breakout_set_column(pool, col, 0, mask)
+
+
+def breakout_fill_column(pool, col, mask=None):
+    """BreakoutIntervention.fill_column(col) (breakout.py:412-416): every brick of the column alive again"""
+    _breakout_set_column(pool, col, 1, mask)
+
+
+def _breakout_set_column(pool, col, alive, mask):
+    cfg = pool.config_to_json()
+    n_rows = len(cfg["row_colors"]) if "row_colors" in cfg else 6
+    for r in range(n_rows):
+        pool.set_property("bricks[%d].alive" % (col * n_rows + r), alive, mask)
+
+
+def breakout_channel_count(pool):
+    """channels per env (column with every brick dead), as ctoybox's breakout_channel_count query: int32[N]"""
+    import torch
+    cfg = pool.config_to_json()
+    n_rows = len(cfg["row_colors"]) if "row_colors" in cfg else 6
+    total = torch.zeros(pool.n_envs, dtype=torch.int32, device=pool.device)
+    for c in range(18):
+        alive = torch.zeros(pool.n_envs, dtype=torch.bool, device=pool.device)
+        for r in range(n_rows):
+            alive |= pool.get_property("bricks[%d].alive" % (c * n_rows + r))
+        total += (~alive).int()
+    return total
+
+
+def amidar_set_mode(pool, mode, time=None, mask=None):
+    """AmidarIntervention.set_mode (toybox/interventions/amidar.py:406-419): 'jump' / 'chase' start the mode's timer
+    (the config's jump_time / chase_time unless `time` is given), 'regular' clears both."""
+    cfg = pool.config_to_json()
+    if mode == "jump":
+        pool.set_property("jump_timer", cfg["jump_time"] if time is None else time, mask)
+    elif mode == "chase":
+        pool.set_property("chase_timer", cfg["chase_time"] if time is None else time, mask)
+    elif mode == "regular":
+        pool.set_property("jump_timer", 0, mask)
+        pool.set_property("chase_timer", 0, mask)
+    else:
+        raise ValueError("mode must be 'jump', 'chase' or 'regular'")

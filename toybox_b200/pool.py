@@ -232,6 +232,45 @@ class BatchedToybox:
         _lib.check(self.L.tbx_stats_read(self._h, out, int(reset), _stream(self.device)))
         return [int(v) for v in out]
 
+    # ------------------------------------------------------------------ vectorised properties (no JSON round trip)
+    def property_info(self, path):
+        """(word, kind, bit) of a scalar of the state schema; kind: 0 int32, 1 float64, 2 bool, 3 bit, 4 Option<i32>."""
+        w, k, b = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.L.tbx_field_lookup(self.game_name.encode(), path.encode(), C.byref(w), C.byref(k), C.byref(b)))
+        return w.value, k.value, b.value
+
+    def get_property(self, path):
+        """`get_property(path)` of toybox/interventions/core.py:285-304 for EVERY env: a device tensor [N] (float64 for the
+        f64 fields, bool for booleans, int32 otherwise; Option<i32> None reads as INT32_MIN)."""
+        _, kind, _ = self.property_info(path)
+        out = torch.empty(self.n_envs, dtype=torch.float64 if kind == 1 else torch.int32, device=self.device)
+        _lib.check(self.L.tbx_field_get(self._h, path.encode(), _ptr(out), _stream(self.device)))
+        return out.bool() if kind in (2, 3) else out
+
+    def set_property(self, path, values, mask=None):
+        """Write one scalar of the state schema for every env (or the envs flagged in `mask`): `values` is a python scalar
+        or a tensor/array of N values; None writes an Option<i32> None."""
+        _, kind, _ = self.property_info(path)
+        dt = torch.float64 if kind == 1 else torch.int32
+        if values is None:
+            if kind != 4:
+                raise ValueError("%s is not an Option field" % path)
+            values = -2 ** 31
+        if torch.is_tensor(values):
+            v = values.to(device=self.device, dtype=dt).contiguous()
+        elif np.ndim(values) == 0:
+            v = torch.full((self.n_envs,), values, dtype=dt, device=self.device)
+        else:
+            v = torch.as_tensor(np.ascontiguousarray(values), device=self.device).to(dt).contiguous()
+        if v.numel() != self.n_envs:
+            raise ValueError("expected %d values" % self.n_envs)
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if m.numel() != self.n_envs:
+                raise ValueError("expected a mask of %d entries" % self.n_envs)
+        _lib.check(self.L.tbx_field_set(self._h, path.encode(), _ptr(v), _ptr(m), _stream(self.device)))
+
     # ------------------------------------------------------------------ JSON (interventions)
     def to_state_json(self, env_ids=None):
         ids = np.arange(self.n_envs, dtype=np.int32) if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
