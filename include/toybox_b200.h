@@ -120,6 +120,9 @@ int tbx_stats_read(tbx_pool *pool, int64_t *out_host, int reset, void *stream);
 /* The synthetic random-action stream of the benchmark and parity tests: fills actions_dev[i] with
  * legal[index(seed, env0 + i, t)] for the pool's game (counter-based, reproducible on the CPU). */
 int tbx_fill_actions(tbx_pool *pool, int32_t *actions_dev, uint64_t seed, uint64_t env0, uint64_t t, void *stream);
+/* The same with the frame counter t read from device memory (*t_dev) when the kernel runs: a CUDA graph that captured
+ * fill + step + render then advances the action stream on every replay (the caller increments *t_dev in the graph). */
+int tbx_fill_actions_at(tbx_pool *pool, int32_t *actions_dev, uint64_t seed, uint64_t env0, const uint64_t *t_dev, void *stream);
 
 /* Benchmark utility: scripted actions computed on the device from the envs' own state.  policy 1 = Breakout
  * "track the ball" (FIRE to serve, then follow the first ball with a varying aim offset), which drives games deep

@@ -279,3 +279,42 @@ def test_delta_render_mixed_states_in_one_chunk(tbx, oracle_mod):
     pool.write_state_json(states)
     check_frames(pool, ref, n)
     pool.close()
+
+
+def test_cuda_graph_replay_equals_stepwise_launches(tbx, oracle_mod):
+    """fill_actions (frame counter in device memory) + step + render captured in a CUDA graph and replayed == the same
+    steps launched one by one, and == the oracle"""
+    import torch
+    n, steps = 64, 40
+    a = tbx.BatchedToybox("breakout", n, seeds=3)
+    b = tbx.BatchedToybox("breakout", n, seeds=3)
+    ref = oracle_mod.OracleBatch("breakout", n, seeds=3 + np.arange(n))
+    dev = a.device
+    acts_a = torch.empty(n, dtype=torch.int32, device=dev)
+    acts_b = torch.empty(n, dtype=torch.int32, device=dev)
+    obs_a = torch.empty((n,) + a.obs_shape, dtype=torch.uint8, device=dev)
+    obs_b = torch.empty_like(obs_a)
+    a.fill_random_actions(acts_a, 0xB200, 0)
+    a.render(out=obs_a)                                   # everything the render path allocates exists before the capture
+    t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            a.fill_random_actions(acts_a, 0xB200, t_dev)
+            t_dev += 1
+            a.apply_ale_action(acts_a, auto_reset=True)
+            a.render(out=obs_a)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    legal = np.asarray(a.get_legal_action_set(), np.int32)
+    for t in range(steps):
+        g.replay()
+        b.fill_random_actions(acts_b, 0xB200, t)
+        b.apply_ale_action(acts_b, auto_reset=True)
+        b.render(out=obs_b)
+        ref.step(legal[[oracle_mod.action_index(0xB200, i, t, len(legal)) for i in range(n)]], auto_reset=True)
+        assert torch.equal(acts_a, acts_b) and torch.equal(obs_a, obs_b), t
+    assert int(t_dev.item()) == steps
+    assert np.array_equal(obs_a.cpu().numpy().reshape(n, -1), ref.render("gray84").reshape(n, -1))
+    a.close(); b.close()

@@ -76,6 +76,7 @@ def lib():
         "tbx_free_str": (None, [vp]),
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
+        "tbx_fill_actions_at": (i32, [vp, vp, u64, u64, vp, vp]),
         "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
         "tbx_field_lookup": (i32, [cp, cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "tbx_field_get": (i32, [vp, cp, vp, vp]),
@@ -97,7 +98,7 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
            "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy",
-           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set"]
+           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set", "tbx_fill_actions_at"]
 
 
 def check(rc):

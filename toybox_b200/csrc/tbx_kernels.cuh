@@ -92,6 +92,12 @@ __global__ void fill_actions_kernel(int32_t *actions, int n, uint64_t seed, uint
   if (i >= n) return;
   actions[i] = legal[tbx_action_index(seed, env0 + (uint64_t)i, t, (uint32_t)n_legal)];
 }
+/* the same with the frame counter read from device memory, so that a captured CUDA graph advances the stream on replay */
+__global__ void fill_actions_at_kernel(int32_t *actions, int n, uint64_t seed, uint64_t env0, const uint64_t *t, const int32_t *legal, int n_legal) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  actions[i] = legal[tbx_action_index(seed, env0 + (uint64_t)i, *t, (uint32_t)n_legal)];
+}
 /* A scripted Breakout policy for benchmarking states deep into a game (the random stream rarely breaks a brick):
  * FIRE while waiting for a serve, otherwise move the paddle under the first ball with a slowly varying aim
  * offset so every paddle segment gets used. */

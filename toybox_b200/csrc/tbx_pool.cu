@@ -607,6 +607,14 @@ int tbx_fill_actions(tbx_pool *p, int32_t *actions, uint64_t seed, uint64_t env0
   return TBX_OK;
 }
 
+int tbx_fill_actions_at(tbx_pool *p, int32_t *actions, uint64_t seed, uint64_t env0, const uint64_t *t_dev, void *stream) {
+  if (!p || !actions || !t_dev) return set_err(TBX_EINVAL, "pool/actions/t_dev is NULL");
+  CK(cudaSetDevice(p->device));
+  fill_actions_at_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(actions, p->n, seed, env0, t_dev, p->d_legal, p->info->n_legal);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
 int tbx_fill_actions_policy(tbx_pool *p, int32_t *actions, int policy, uint64_t t, void *stream) {
   if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
   if (policy != 1 || p->game != TBX_BREAKOUT) return set_err(TBX_EINVAL, "only policy 1 (Breakout ball tracking) is implemented");

@@ -197,8 +197,12 @@ class BatchedToybox:
         return obs_out, r, d, {"score": s, "lives": l}
 
     def fill_random_actions(self, out, seed, t, env0=0):
-        """The benchmark's reproducible uniform-over-legal action stream, generated on the device."""
-        _lib.check(self.L.tbx_fill_actions(self._h, _ptr(out), int(seed), int(env0), int(t), _stream(self.device)))
+        """The benchmark's reproducible uniform-over-legal action stream, generated on the device.  `t` is the
+        frame index: a python int, or a one-element int64 device tensor read when the kernel runs (CUDA-graph replays)."""
+        if torch.is_tensor(t):
+            _lib.check(self.L.tbx_fill_actions_at(self._h, _ptr(out), int(seed), int(env0), _ptr(t), _stream(self.device)))
+        else:
+            _lib.check(self.L.tbx_fill_actions(self._h, _ptr(out), int(seed), int(env0), int(t), _stream(self.device)))
         return out
 
     def fill_policy_actions(self, out, policy, t):
