@@ -54,3 +54,26 @@ def test_area_render_paths_bit_exact(tbx, oracle_mod, game):
     finally:
         _set_env({})
         pool.close()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_native_render_paths_bit_exact(tbx, oracle_mod, game):
+    """native layouts: broadcast + patch (list, sweep and per-tile rebuild paths) and the canvas kernel"""
+    n = 45
+    pool, ref = _advance(tbx, oracle_mod, game, n, 1200 if game == "breakout" else 400, 78)
+    keys = ("TBX_AREA_LCAP", "TBX_NATIVE_KERNEL")
+    try:
+        for mode in ("rgb", "rgba", "gray"):
+            want = ref.render(mode).reshape(n, -1)
+            for v in ({}, {"TBX_NATIVE_KERNEL": "patch"}, {"TBX_NATIVE_KERNEL": "patch", "TBX_AREA_LCAP": "24"},
+                      {"TBX_NATIVE_KERNEL": "patch", "TBX_AREA_LCAP": "3"}, {"TBX_NATIVE_KERNEL": "canvas"}):
+                for k in keys:
+                    os.environ.pop(k, None)
+                os.environ.update(v)
+                got = pool.render(obs=mode).cpu().numpy().reshape(n, -1)
+                bad = np.argwhere(got != want)
+                assert bad.size == 0, (game, mode, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+        pool.close()

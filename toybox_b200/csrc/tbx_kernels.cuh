@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include "tbx_render.cuh"
 #include "tbx_render_area.cuh"
+#include "tbx_render_native.cuh"
 #include "tbx_host.h"
 
 namespace tbxk {

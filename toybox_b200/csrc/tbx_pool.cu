@@ -320,6 +320,38 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
   CK(cudaGetLastError());
   return TBX_OK;
 }
+/* native layouts as broadcast + patch (tbx_render_native.cuh) */
+template <int GAME, int PIX> static int launch_native_pix(const tbx_pool *p, const RenderArgs &a, const void *cfg_host, int band_smem, cudaStream_t s) {
+  typedef typename Traits<GAME>::Cfg Cfg;
+  static int configured = 0;
+  const int threads = 256;
+  const int patch_smem = a.smem_canvas + (threads / 32) * a.warp_bytes;
+  if (!configured) {
+    CK((cudaFuncSetAttribute(base_fill_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)));
+    CK((cudaFuncSetAttribute(native_patch_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
+    configured = 1;
+  }
+  if (band_smem > 64 * 1024 || patch_smem > 160 * 1024) return set_err(TBX_EINVAL, "frame too wide for the native render path");
+  const int H = Traits<GAME>::H;
+  dim3 grid(blocks(a.n, TBX_FILL_ENVS), (H + a.band_rows - 1) / a.band_rows);
+  base_fill_kernel<GAME, PIX><<<grid, 128, band_smem, s>>>(a, *(const Cfg *)cfg_host);
+  CK(cudaGetLastError());
+  native_patch_kernel<GAME, PIX><<<blocks(a.n, TBX_EPC), threads, patch_smem, s>>>(a, *(const Cfg *)cfg_host);
+  CK(cudaGetLastError());
+  (void)p;
+  return TBX_OK;
+}
+template <int GAME> static int launch_native_game(const tbx_pool *p, int mode, const RenderArgs &a, const void *c, int band_smem, cudaStream_t s) {
+  if (mode == TBX_OBS_RGBA) return launch_native_pix<GAME, 4>(p, a, c, band_smem, s);
+  if (mode == TBX_OBS_RGB) return launch_native_pix<GAME, 3>(p, a, c, band_smem, s);
+  return launch_native_pix<GAME, 1>(p, a, c, band_smem, s);
+}
+static int launch_native(const tbx_pool *p, int mode, const RenderArgs &a, int band_smem, cudaStream_t s) {
+  if (p->game == TBX_BREAKOUT) return launch_native_game<TBX_BREAKOUT>(p, mode, a, cfg_ptr(p), band_smem, s);
+  if (p->game == TBX_AMIDAR) return launch_native_game<TBX_AMIDAR>(p, mode, a, cfg_ptr(p), band_smem, s);
+  return launch_native_game<TBX_SPACE_INVADERS>(p, mode, a, cfg_ptr(p), band_smem, s);
+}
+
 /* INTER_AREA, one warp per env (tbx_render_area.cuh) */
 template <int GAME, int TX, int TY> static int launch_area_tile(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
   static int configured = 0;
@@ -456,6 +488,22 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
     }
     a.smem_rects = a.smem_canvas + align16(canvas_rows * W + 16);
   } else {
+    /* Two renderers (TBX_NATIVE_KERNEL=patch|canvas overrides): broadcast + patch (tbx_render_native.cuh) wins where few
+     * pixels differ from the base frame (Amidar RGB 22.8 -> 35.3 M frames/s), the canvas kernel below where an env
+     * repaints ~50 sprites (Space Invaders 15.1 vs 10.1) or in mid-game Breakout; Breakout's fresh games are a tie. */
+    const char *ksel = getenv("TBX_NATIVE_KERNEL");
+    const bool patch = ksel ? !strcmp(ksel, "patch") : p->game == TBX_AMIDAR;
+    if (patch && !dual) {
+      int max_rows = (40 * 1024) / (W * pix);
+      if (max_rows < 1) max_rows = 1;
+      const int nb = (H + max_rows - 1) / max_rows;
+      a.band_rows = (H + nb - 1) / nb;
+      a.list_cap = TBX_NT_LCAP;
+      if (const char *env = getenv("TBX_AREA_LCAP")) a.list_cap = atoi(env);
+      if (a.list_cap < 1 || a.list_cap > TBX_NT_LCAP) a.list_cap = TBX_NT_LCAP;
+      a.warp_bytes = align16(TBX_NT_LCAP * 24 + 64 + TBX_NT_MAX_RUN(pix) * TBX_NT_TW * pix * TBX_NT_TH);
+      return launch_native(p, mode, a, align16(a.band_rows * W * pix), (cudaStream_t)stream);
+    }
     /* canvas bands of at most ~40 KB so that five CTAs stay resident per SM */
     int max_rows = (40 * 1024) / (W * pix);
     if (max_rows < 1) max_rows = 1;
