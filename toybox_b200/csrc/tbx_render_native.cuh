@@ -13,6 +13,8 @@
  *      small scratch, paints the hit entries in draw order (painter's algorithm, identical result) and overwrites the
  *      window's bytes in the frame.  Work and traffic are proportional to what differs from the base.
  * Same list / sweep / rebuild machinery as tbx_render_area.cuh, in native pixel space and in the output pixel format.
+ * (Measured and dropped: both steps fused per (8 envs, band) CTA -- 100+ registers, the patches wait for the stores to
+ * LAND and every band rebuilds the entries: Amidar RGB 24.7 M frames/s against 35.3 M for the two launches.)
  */
 #ifndef TBX_RENDER_NATIVE_CUH
 #define TBX_RENDER_NATIVE_CUH
@@ -140,6 +142,180 @@ __device__ __forceinline__ void mark_native_tiles(uint32_t *tmask, const uint2 &
   for (int ty = y0 / TBX_NT_TH; ty <= (y1 - 1) / TBX_NT_TH; ty++) atomicOr(&tmask[ty >> 1], cols << ((ty & 1) * 16));
 }
 
+/* the patches of one env over tile rows [ty_lo, ty_hi): every lane of the warp calls it */
+template <int GAME, int PIX>
+__device__ __forceinline__ void patch_env(const RenderArgs &a, const uint32_t *R, const typename Traits<GAME>::Cfg &cfg, const typename Traits<GAME>::Table *tables,
+                                          int ty_lo, int ty_hi, uint8_t *out, uint4 *list, uint2 *exts, uint32_t *tmask, uint8_t *scr, int lane) {
+  typedef Traits<GAME> T;
+  constexpr int W = T::W, H = T::H;
+  constexpr int STRIDE = TBX_NT_MAX_RUN(PIX) * TBX_NT_TW * PIX;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int base = T::base_id(R, cfg, tables);
+  const uint8_t *bfr = base ? a.base[1] : a.base[0];
+  const int nty = ty_hi - ty_lo;
+  int nsw = 1;
+  for (int sw = 0; sw < nsw; sw++) {
+    const int tyA = ty_lo + (sw * nty) / nsw, tyB = ty_lo + ((sw + 1) * nty) / nsw;
+    if (tyA >= tyB) continue;
+    const int rA = tyA * TBX_NT_TH, rB = min(H, tyB * TBX_NT_TH);
+    __syncwarp();
+    if (lane < 16) tmask[lane] = 0;
+    __syncwarp();
+    int n = 0;
+    bool overflow = false;
+    for (int g = 0; g < T::NG && !overflow; g++) {
+      int gb, ge, gmode;
+      T::group(g, R, tables, base, gb, ge, gmode);
+      T::trim(g, R, cfg, base, gb, ge);
+      for (int s0 = gb; s0 < ge; s0 += 32) {
+        const int s = s0 + lane;
+        TbxPrim p = tbx_prim_none();
+        if (s < ge) p = T::prim(R, cfg, tables, s, base);
+        uint4 e;
+        uint2 ext;
+        const bool ok = make_native_entry<W, PIX>(p, g, gmode, rA, rB, e, ext);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m == 0) continue;
+        if (n + __popc(m) > a.list_cap) { overflow = true; break; }
+        if (ok) {
+          const int slot = n + __popc(m & lt_mask);
+          list[slot] = e;
+          exts[slot] = ext;
+          mark_native_tiles(tmask, ext);
+        }
+        n += __popc(m);
+      }
+    }
+    if (overflow && nsw < nty) { nsw = min(nty, nsw * 2); sw = -1; continue; }
+    __syncwarp();
+    if (overflow) {
+      /* one tile row with more entries than the list holds: rebuild the primitives per tile, paint in draw order */
+      const int wy0 = rA, wy1 = rB;
+      for (int wx0 = 0; wx0 < W; wx0 += TBX_NT_TW) {
+        const int wx1 = min(W, wx0 + TBX_NT_TW);
+        const int nwr = ((wx1 - wx0) * PIX) >> 2;
+        for (int y = 0; y < wy1 - wy0; y++)
+          for (int c = lane; c < nwr; c += 32)
+            reinterpret_cast<uint32_t *>(scr + y * STRIDE)[c] = __ldg(reinterpret_cast<const uint32_t *>(bfr + ((size_t)(wy0 + y) * W + wx0) * PIX) + c);
+        __syncwarp();
+        for (int g = 0; g < T::NG; g++) {
+          int gb, ge, gmode;
+          T::group(g, R, tables, base, gb, ge, gmode);
+          T::trim(g, R, cfg, base, gb, ge);
+          for (int s0 = gb; s0 < ge; s0 += 32) {
+            const int s = s0 + lane;
+            TbxPrim p = tbx_prim_none();
+            if (s < ge) p = T::prim(R, cfg, tables, s, base);
+            uint4 e;
+            uint2 ext;
+            bool hit = make_native_entry<W, PIX>(p, g, gmode, rA, rB, e, ext);
+            hit = hit && (int)(ext.x & 0xffffu) < wx1 && (int)(ext.x >> 16) > wx0;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+              const int l = __ffs(m) - 1;
+              m &= m - 1;
+              uint4 q;
+              q.x = __shfl_sync(0xffffffffu, e.x, l); q.y = __shfl_sync(0xffffffffu, e.y, l);
+              q.z = __shfl_sync(0xffffffffu, e.z, l); q.w = __shfl_sync(0xffffffffu, e.w, l);
+              paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
+              __syncwarp();
+            }
+          }
+        }
+        for (int y = 0; y < wy1 - wy0; y++)
+          for (int c = lane; c < nwr; c += 32)
+            reinterpret_cast<uint32_t *>(out + ((size_t)(wy0 + y) * W + wx0) * PIX)[c] = reinterpret_cast<const uint32_t *>(scr + y * STRIDE)[c];
+        __syncwarp();
+      }
+      continue;
+    }
+    if (n == 0) continue;
+
+    /* the marked tiles, one run of horizontally adjacent tiles of a tile row at a time */
+    for (int ty = tyA; ty < tyB; ty++) {
+      uint32_t rowbits = (tmask[ty >> 1] >> ((ty & 1) * 16)) & 0xffffu;
+      while (rowbits) {
+        const int t0 = __ffs(rowbits) - 1;
+        const int len = min(__ffs(~(rowbits >> t0)) - 1, TBX_NT_MAX_RUN(PIX));
+        rowbits &= ~(((1u << len) - 1u) << t0);
+        const int rx0 = t0 * TBX_NT_TW, rx1 = min(W, rx0 + len * TBX_NT_TW), ry0 = ty * TBX_NT_TH, ry1 = min(H, ry0 + TBX_NT_TH);
+        uint32_t hm[TBX_NT_LCAP / 32];
+        int bx0 = 65535, bx1 = 0, by0 = 65535, by1 = 0;
+#pragma unroll
+        for (int c = 0; c < TBX_NT_LCAP / 32; c++) {
+          hm[c] = 0;
+          if (c * 32 >= n) continue;
+          bool hit = false;
+          if (c * 32 + lane < n) {
+            const uint2 ext = exts[c * 32 + lane];
+            const int x0 = ext.x & 0xffffu, x1 = ext.x >> 16, y0 = ext.y & 1023u, y1 = (ext.y >> 10) & 1023u;
+            hit = x0 < rx1 && x1 > rx0 && y0 < ry1 && y1 > ry0;
+            if (hit) { bx0 = min(bx0, x0); bx1 = max(bx1, x1); by0 = min(by0, y0); by1 = max(by1, y1); }
+          }
+          hm[c] = __ballot_sync(0xffffffffu, hit);
+        }
+        /* the window: the hit entries' bounding box inside the run, columns widened to multiples of 4 pixels so that
+         * its rows are whole 32-bit words in every pixel format */
+        const int wx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)) & ~3, wx1 = min(rx1, (__reduce_max_sync(0xffffffffu, bx1) + 3) & ~3);
+        const int wy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), wy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
+        if (wx0 >= wx1 || wy0 >= wy1) continue;
+        const int nwr = ((wx1 - wx0) * PIX) >> 2, nrows = wy1 - wy0;
+        {
+          const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
+          const int rstep = 32 >> lg;
+          for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32)
+            for (int y = lane >> lg; y < nrows; y += rstep)
+              reinterpret_cast<uint32_t *>(scr + y * STRIDE)[cc] = __ldg(reinterpret_cast<const uint32_t *>(bfr + ((size_t)(wy0 + y) * W + wx0) * PIX) + cc);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < TBX_NT_LCAP / 32; c++) {
+          uint32_t m = hm[c];
+          if (m == 0) continue;
+          uint4 e = make_uint4(0, 0, 0, 0);
+          uint32_t gf = 0; /* group << 20 | flags << 28 */
+          if ((m >> lane) & 1u) { e = list[c * 32 + lane]; gf = exts[c * 32 + lane].y >> 20; }
+          while (m) {
+            const int l = __ffs(m) - 1;
+            const uint32_t gl = __shfl_sync(0xffffffffu, gf, l);
+            if (!((gl >> 8) & TBX_ENTRY_PAR)) { /* in-order group: one entry at a time */
+              const uint4 q = list[c * 32 + l];
+              paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
+              __syncwarp();
+              m &= m - 1;
+              continue;
+            }
+            const bool mine = ((m >> lane) & 1u) && (gf & 255u) == (gl & 255u);
+            const uint32_t same = __ballot_sync(0xffffffffu, mine);
+            bool small = mine && ((gf >> 8) & TBX_ENTRY_SMALL);
+            uint32_t smalls = __ballot_sync(0xffffffffu, small);
+            if (__popc(smalls) < 3) { smalls = 0; small = false; }
+            uint32_t big = same & ~smalls;
+            if (small) paint_window_lane<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, e);
+            __syncwarp();
+            while (big) {
+              const int lb = __ffs(big) - 1;
+              big &= big - 1;
+              const uint4 q = list[c * 32 + lb];
+              paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
+              __syncwarp();
+            }
+            m &= ~same;
+          }
+        }
+        { /* overwrite the window in the frame */
+          const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
+          const int rstep = 32 >> lg;
+          for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32)
+            for (int y = lane >> lg; y < nrows; y += rstep)
+              reinterpret_cast<uint32_t *>(out + ((size_t)(wy0 + y) * W + wx0) * PIX)[cc] = reinterpret_cast<const uint32_t *>(scr + y * STRIDE)[cc];
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 template <int GAME, int PIX>
 __global__ void __launch_bounds__(256, 4) native_patch_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ typename Traits<GAME>::Cfg cfg_c) {
   typedef Traits<GAME> T;
@@ -166,175 +342,9 @@ __global__ void __launch_bounds__(256, 4) native_patch_kernel(const __grid_const
   uint2 *exts = reinterpret_cast<uint2 *>(wmem + TBX_NT_LCAP * 16);
   uint32_t *tmask = reinterpret_cast<uint32_t *>(wmem + TBX_NT_LCAP * 24);
   uint8_t *scr = wmem + TBX_NT_LCAP * 24 + 64;
-  const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (int j = wid; j < ne; j += nwarps) {
-    const uint32_t *R = recs + j * RW;
-    const int base = T::base_id(R, cfg, tables);
-    const uint8_t *bfr = base ? a.base[1] : a.base[0];
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
-    int nsw = 1;
-    for (int sw = 0; sw < nsw; sw++) {
-      const int tyA = (sw * NTY) / nsw, tyB = ((sw + 1) * NTY) / nsw;
-      if (tyA >= tyB) continue;
-      const int rA = tyA * TBX_NT_TH, rB = min(H, tyB * TBX_NT_TH);
-      __syncwarp();
-      if (lane < 16) tmask[lane] = 0;
-      __syncwarp();
-      int n = 0;
-      bool overflow = false;
-      for (int g = 0; g < T::NG && !overflow; g++) {
-        int gb, ge, gmode;
-        T::group(g, R, tables, base, gb, ge, gmode);
-        T::trim(g, R, cfg, base, gb, ge);
-        for (int s0 = gb; s0 < ge; s0 += 32) {
-          const int s = s0 + lane;
-          TbxPrim p = tbx_prim_none();
-          if (s < ge) p = T::prim(R, cfg, tables, s, base);
-          uint4 e;
-          uint2 ext;
-          const bool ok = make_native_entry<W, PIX>(p, g, gmode, rA, rB, e, ext);
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (m == 0) continue;
-          if (n + __popc(m) > a.list_cap) { overflow = true; break; }
-          if (ok) {
-            const int slot = n + __popc(m & lt_mask);
-            list[slot] = e;
-            exts[slot] = ext;
-            mark_native_tiles(tmask, ext);
-          }
-          n += __popc(m);
-        }
-      }
-      if (overflow && nsw < NTY) { nsw = min(NTY, nsw * 2); sw = -1; continue; }
-      __syncwarp();
-      if (overflow) {
-        /* one tile row with more entries than the list holds: rebuild the primitives per tile, paint in draw order */
-        const int wy0 = rA, wy1 = rB;
-        for (int wx0 = 0; wx0 < W; wx0 += TBX_NT_TW) {
-          const int wx1 = min(W, wx0 + TBX_NT_TW);
-          const int nwr = ((wx1 - wx0) * PIX) >> 2;
-          for (int y = 0; y < wy1 - wy0; y++)
-            for (int c = lane; c < nwr; c += 32)
-              reinterpret_cast<uint32_t *>(scr + y * STRIDE)[c] = __ldg(reinterpret_cast<const uint32_t *>(bfr + ((size_t)(wy0 + y) * W + wx0) * PIX) + c);
-          __syncwarp();
-          for (int g = 0; g < T::NG; g++) {
-            int gb, ge, gmode;
-            T::group(g, R, tables, base, gb, ge, gmode);
-            T::trim(g, R, cfg, base, gb, ge);
-            for (int s0 = gb; s0 < ge; s0 += 32) {
-              const int s = s0 + lane;
-              TbxPrim p = tbx_prim_none();
-              if (s < ge) p = T::prim(R, cfg, tables, s, base);
-              uint4 e;
-              uint2 ext;
-              bool hit = make_native_entry<W, PIX>(p, g, gmode, rA, rB, e, ext);
-              hit = hit && (int)(ext.x & 0xffffu) < wx1 && (int)(ext.x >> 16) > wx0;
-              unsigned m = __ballot_sync(0xffffffffu, hit);
-              while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                uint4 q;
-                q.x = __shfl_sync(0xffffffffu, e.x, l); q.y = __shfl_sync(0xffffffffu, e.y, l);
-                q.z = __shfl_sync(0xffffffffu, e.z, l); q.w = __shfl_sync(0xffffffffu, e.w, l);
-                paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
-                __syncwarp();
-              }
-            }
-          }
-          for (int y = 0; y < wy1 - wy0; y++)
-            for (int c = lane; c < nwr; c += 32)
-              reinterpret_cast<uint32_t *>(out + ((size_t)(wy0 + y) * W + wx0) * PIX)[c] = reinterpret_cast<const uint32_t *>(scr + y * STRIDE)[c];
-          __syncwarp();
-        }
-        continue;
-      }
-      if (n == 0) continue;
-
-      /* the marked tiles, one run of horizontally adjacent tiles of a tile row at a time */
-      for (int ty = tyA; ty < tyB; ty++) {
-        uint32_t rowbits = (tmask[ty >> 1] >> ((ty & 1) * 16)) & 0xffffu;
-        while (rowbits) {
-          const int t0 = __ffs(rowbits) - 1;
-          const int len = min(__ffs(~(rowbits >> t0)) - 1, TBX_NT_MAX_RUN(PIX));
-          rowbits &= ~(((1u << len) - 1u) << t0);
-          const int rx0 = t0 * TBX_NT_TW, rx1 = min(W, rx0 + len * TBX_NT_TW), ry0 = ty * TBX_NT_TH, ry1 = min(H, ry0 + TBX_NT_TH);
-          uint32_t hm[TBX_NT_LCAP / 32];
-          int bx0 = 65535, bx1 = 0, by0 = 65535, by1 = 0;
-#pragma unroll
-          for (int c = 0; c < TBX_NT_LCAP / 32; c++) {
-            hm[c] = 0;
-            if (c * 32 >= n) continue;
-            bool hit = false;
-            if (c * 32 + lane < n) {
-              const uint2 ext = exts[c * 32 + lane];
-              const int x0 = ext.x & 0xffffu, x1 = ext.x >> 16, y0 = ext.y & 1023u, y1 = (ext.y >> 10) & 1023u;
-              hit = x0 < rx1 && x1 > rx0 && y0 < ry1 && y1 > ry0;
-              if (hit) { bx0 = min(bx0, x0); bx1 = max(bx1, x1); by0 = min(by0, y0); by1 = max(by1, y1); }
-            }
-            hm[c] = __ballot_sync(0xffffffffu, hit);
-          }
-          /* the window: the hit entries' bounding box inside the run, columns widened to multiples of 4 pixels so that
-           * its rows are whole 32-bit words in every pixel format */
-          const int wx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)) & ~3, wx1 = min(rx1, (__reduce_max_sync(0xffffffffu, bx1) + 3) & ~3);
-          const int wy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), wy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
-          if (wx0 >= wx1 || wy0 >= wy1) continue;
-          const int nwr = ((wx1 - wx0) * PIX) >> 2, nrows = wy1 - wy0;
-          {
-            const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
-            const int rstep = 32 >> lg;
-            for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32)
-              for (int y = lane >> lg; y < nrows; y += rstep)
-                reinterpret_cast<uint32_t *>(scr + y * STRIDE)[cc] = __ldg(reinterpret_cast<const uint32_t *>(bfr + ((size_t)(wy0 + y) * W + wx0) * PIX) + cc);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < TBX_NT_LCAP / 32; c++) {
-            uint32_t m = hm[c];
-            if (m == 0) continue;
-            uint4 e = make_uint4(0, 0, 0, 0);
-            uint32_t gf = 0; /* group << 20 | flags << 28 */
-            if ((m >> lane) & 1u) { e = list[c * 32 + lane]; gf = exts[c * 32 + lane].y >> 20; }
-            while (m) {
-              const int l = __ffs(m) - 1;
-              const uint32_t gl = __shfl_sync(0xffffffffu, gf, l);
-              if (!((gl >> 8) & TBX_ENTRY_PAR)) { /* in-order group: one entry at a time */
-                const uint4 q = list[c * 32 + l];
-                paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
-                __syncwarp();
-                m &= m - 1;
-                continue;
-              }
-              const bool mine = ((m >> lane) & 1u) && (gf & 255u) == (gl & 255u);
-              const uint32_t same = __ballot_sync(0xffffffffu, mine);
-              bool small = mine && ((gf >> 8) & TBX_ENTRY_SMALL);
-              uint32_t smalls = __ballot_sync(0xffffffffu, small);
-              if (__popc(smalls) < 3) { smalls = 0; small = false; }
-              uint32_t big = same & ~smalls;
-              if (small) paint_window_lane<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, e);
-              __syncwarp();
-              while (big) {
-                const int lb = __ffs(big) - 1;
-                big &= big - 1;
-                const uint4 q = list[c * 32 + lb];
-                paint_window<PIX>(scr, STRIDE, wx0, wy0, wx1, wy1, q, R, lane);
-                __syncwarp();
-              }
-              m &= ~same;
-            }
-          }
-          { /* overwrite the window in the frame */
-            const int lg = nwr > 16 ? 5 : nwr > 8 ? 4 : nwr > 4 ? 3 : 2;
-            const int rstep = 32 >> lg;
-            for (int cc = lane & ((1 << lg) - 1); cc < nwr; cc += 32)
-              for (int y = lane >> lg; y < nrows; y += rstep)
-                reinterpret_cast<uint32_t *>(out + ((size_t)(wy0 + y) * W + wx0) * PIX)[cc] = reinterpret_cast<const uint32_t *>(scr + y * STRIDE)[cc];
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
+  for (int j = wid; j < ne; j += nwarps)
+    patch_env<GAME, PIX>(a, recs + j * RW, cfg, tables, 0, NTY, a.dst + (size_t)(e0 + j) * a.frame_bytes, list, exts, tmask, scr, lane);
 }
 
 } /* namespace tbxk */
