@@ -13,7 +13,8 @@
  *      small scratch, paints the hit entries in draw order (painter's algorithm, identical result) and overwrites the
  *      window's bytes in the frame.  Work and traffic are proportional to what differs from the base.
  * Same list / sweep / rebuild machinery as tbx_render_area.cuh, in native pixel space and in the output pixel format.
- * (Measured and dropped: both steps fused per (8 envs, band) CTA -- 100+ registers, the patches wait for the stores to
+ * (Measured and dropped: the patches of env chunk c on a second stream while chunk c+1 is broadcast -- no gain
+ * with 2, 4 or 8 chunks, even with the broadcast CTAs padded to 104 KB of shared memory so that both grids fit an SM; and both steps fused per (8 envs, band) CTA -- 100+ registers, the patches wait for the stores to
  * LAND and every band rebuilds the entries: Amidar RGB 24.7 M frames/s against 35.3 M for the two launches.)
  */
 #ifndef TBX_RENDER_NATIVE_CUH
@@ -321,7 +322,6 @@ __global__ void __launch_bounds__(256, 4) native_patch_kernel(const __grid_const
   typedef Traits<GAME> T;
   constexpr int W = T::W, H = T::H, RW = T::RW;
   constexpr int NTY = (H + TBX_NT_TH - 1) / TBX_NT_TH; /* tile rows (<= 32) */
-  constexpr int STRIDE = TBX_NT_MAX_RUN(PIX) * TBX_NT_TW * PIX;
   static_assert(NTY <= 32 && (W + TBX_NT_TW - 1) / TBX_NT_TW <= 16, "tile mask layout");
   extern __shared__ uint4 smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
