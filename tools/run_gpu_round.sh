@@ -20,7 +20,9 @@ cap() { # name kernel-regex traffic-key bench-args...
 cap area_brk area_tile breakout/gray84/65536 --game breakout
 cap step_brk step_kernel breakout/step/65536 --game breakout
 cap rgba_brk render_kernel breakout/rgba/65536 --game breakout --obs rgba
-cap rgb_amidar render_kernel amidar/rgb/65536 --game amidar --obs rgb
+cap fill_amidar base_fill amidar/rgb-fill/65536 --game amidar --obs rgb
+cap patch_amidar native_patch amidar/rgb-patch/65536 --game amidar --obs rgb
+cap rgb_si render_kernel space_invaders/rgb/65536 --game space_invaders --obs rgb
 cap area_amidar area_tile amidar/gray84/65536 --game amidar
 cap area_si area_tile space_invaders/gray84/65536 --game space_invaders
 rm -f gpurun_out/${TAG}_prof_*.ncu-rep
