@@ -353,15 +353,19 @@ static int launch_native(const tbx_pool *p, int mode, const RenderArgs &a, int b
 }
 
 /* INTER_AREA, one warp per env (tbx_render_area.cuh) */
-template <int GAME, int TX, int TY> static int launch_area_tile(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
+template <int GAME, int TX, int TY, bool DUAL> static int launch_area_tile_dual(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
   static int configured = 0;
   if (configured < smem) {
-    CK((cudaFuncSetAttribute(area_tile_kernel<GAME, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    CK((cudaFuncSetAttribute(area_tile_kernel<GAME, TX, TY, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     configured = smem;
   }
-  area_tile_kernel<GAME, TX, TY><<<blocks(a.n, TBX_EPC), threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, *plan_host);
+  area_tile_kernel<GAME, TX, TY, DUAL><<<blocks(a.n, TBX_EPC), threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, *plan_host);
   CK(cudaGetLastError());
   return TBX_OK;
+}
+template <int GAME, int TX, int TY> static int launch_area_tile(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
+  if (a.planes2) return launch_area_tile_dual<GAME, TX, TY, true>(a, cfg_host, plan_host, smem, threads, s);
+  return launch_area_tile_dual<GAME, TX, TY, false>(a, cfg_host, plan_host, smem, threads, s);
 }
 template <int GAME> static int launch_area_tile_taps(int tx, int ty, const RenderArgs &a, const void *c, const TbxAreaPlan *pl, int smem, int threads, cudaStream_t s) {
   if (ty <= 3) {

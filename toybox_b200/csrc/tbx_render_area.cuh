@@ -223,7 +223,7 @@ __device__ __noinline__ void tile_row_rebuild(const uint32_t *R, const uint32_t 
   }
 }
 
-template <int GAME, int TX, int TY>
+template <int GAME, int TX, int TY, bool DUAL>
 __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_tile_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ typename Traits<GAME>::Cfg cfg_c,
                                                                          const __grid_constant__ TbxAreaPlan plan_c) {
   typedef Traits<GAME> T;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
   const int ne = min(TBX_EPC, a.n - e0);
-  const bool dual = a.planes2 != 0; /* observation = down-sample of max(frame of planes, frame of planes2) */
+  constexpr bool dual = DUAL; /* observation = down-sample of max(frame of planes, frame of planes2): a.planes2 != NULL */
   uint32_t *recs2 = recs + RW * TBX_EPC;
   for (int i = tid; i < RW * TBX_EPC; i += blockDim.x) {
     const int w = i / TBX_EPC, j = i - w * TBX_EPC;
