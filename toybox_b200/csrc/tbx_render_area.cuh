@@ -295,20 +295,18 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       __syncwarp();
       int n = 0;
       bool overflow = false;
-      for (int st = 0; st < (dual ? 2 : 1) && !overflow; st++) {
-        const uint32_t *Rs = st ? R2 : R;
-        const int bs = st ? base2 : base;
+      if constexpr (!dual) {
         for (int g = 0; g < T::NG && !overflow; g++) {
           int gb, ge, gmode;
-          T::group(g, Rs, tables, bs, gb, ge, gmode);
-          T::trim(g, Rs, cfg, bs, gb, ge);
+          T::group(g, R, tables, base, gb, ge, gmode);
+          T::trim(g, R, cfg, base, gb, ge);
           for (int s0 = gb; s0 < ge; s0 += 32) {
             const int s = s0 + lane;
             TbxPrim p = tbx_prim_none();
-            if (s < ge) p = T::prim(Rs, cfg, tables, s, bs);
+            if (s < ge) p = T::prim(R, cfg, tables, s, base);
             uint4 e;
             uint32_t ext;
-            const bool ok = make_entry<W>(p, g | (st << 7), gmode, rA, rB, dyA, dyB, plan, e, ext);
+            const bool ok = make_entry<W>(p, g, gmode, rA, rB, dyA, dyB, plan, e, ext);
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (m == 0) continue;
             if (n + __popc(m) > a.list_cap) { overflow = true; break; }
@@ -319,6 +317,48 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
               mark_tiles(tmask, ext, ths);
             }
             n += __popc(m);
+          }
+        }
+      } else {
+        /* Both states in one pass over the slots.  A slot whose primitive is the same in both states (HUD digits,
+         * bricks, most sprites from one frame to the next) becomes ONE entry flagged 0x40 = "in both frames"; a run
+         * hit by such entries only is rendered once.  Otherwise the slot emits its first-state entry, then its
+         * second-state entry (flag 0x80): draw order is preserved within either state. */
+        for (int g = 0; g < T::NG && !overflow; g++) {
+          int gbA, geA, gmA, gbB, geB, gmB;
+          T::group(g, R, tables, base, gbA, geA, gmA);
+          T::trim(g, R, cfg, base, gbA, geA);
+          T::group(g, R2, tables, base2, gbB, geB, gmB);
+          T::trim(g, R2, cfg, base2, gbB, geB);
+          const bool merge = base == base2 && gmA == gmB;
+          const int lo = gbA >= geA ? gbB : gbB >= geB ? gbA : min(gbA, gbB), hi = max(geA, geB);
+          for (int s0 = lo; s0 < hi; s0 += 32) {
+            const int s = s0 + lane;
+            TbxPrim pA = tbx_prim_none(), pB = tbx_prim_none();
+            if (s >= gbA && s < geA) pA = T::prim(R, cfg, tables, s, base);
+            if (s >= gbB && s < geB) pB = T::prim(R2, cfg, tables, s, base2);
+            uint4 eA, eB;
+            uint32_t xA, xB;
+            const bool okA = make_entry<W>(pA, g, gmA, rA, rB, dyA, dyB, plan, eA, xA);
+            const bool okB = make_entry<W>(pB, g | 0x80, gmB, rA, rB, dyA, dyB, plan, eB, xB);
+            const bool both = merge && okA && okB && eA.x == eB.x && eA.y == eB.y && ((eA.z ^ eB.z) & 0xffu) == 0 && eA.w == eB.w &&
+                              !(eA.w & TBX_PRIM_STATE); /* sprites stored in the record may differ bit by bit */
+            const unsigned m1 = __ballot_sync(0xffffffffu, okA), m2 = __ballot_sync(0xffffffffu, okB && !both);
+            if ((m1 | m2) == 0) continue;
+            if (n + __popc(m1) + __popc(m2) > a.list_cap) { overflow = true; break; }
+            const int slot = n + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
+            if (okA) {
+              if (both) eA.z |= 0x40u << 8;
+              list[slot] = eA;
+              exts[slot] = xA;
+              mark_tiles(tmask, xA, ths);
+            }
+            if (okB && !both) {
+              list[slot + (okA ? 1 : 0)] = eB;
+              exts[slot + (okA ? 1 : 0)] = xB;
+              mark_tiles(tmask, xB, ths);
+            }
+            n += __popc(m1) + __popc(m2);
           }
         }
       }
@@ -356,6 +396,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
           const int rx0 = t0 * 16, rx1 = rx0 + len * 16 - 1, ry0 = ty << ths, ry1 = ry0 + (1 << ths) - 1;
           uint32_t hm[TBX_TILE_LCAP / 32];
           int bx0 = 255, bx1 = 0, by0 = 255, by1 = 0;
+          bool two_frames = redo_all; /* dual mode: some hit entry belongs to one frame only (else both frames agree here) */
 #pragma unroll
           for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
             hm[c] = 0;
@@ -365,6 +406,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
             const bool hit = xlo <= rx1 && xhi >= rx0 && ylo <= ry1 && yhi >= ry0;
             hm[c] = __ballot_sync(0xffffffffu, hit);
             if (hit) { bx0 = min(bx0, xlo); bx1 = max(bx1, xhi); by0 = min(by0, ylo); by1 = max(by1, yhi); }
+            if constexpr (dual) two_frames |= __ballot_sync(0xffffffffu, hit && !((list[c * 32 + lane].z >> 8) & 0x40u)) != 0;
           }
           int dx0 = max(rx0, __reduce_min_sync(0xffffffffu, bx0)), dx1 = min(rx1, __reduce_max_sync(0xffffffffu, bx1));
           int dy0 = max(ry0, __reduce_min_sync(0xffffffffu, by0)), dy1 = min(ry1, __reduce_max_sync(0xffffffffu, by1));
@@ -373,7 +415,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
           const int wx0 = cp.xs0[dx0] & ~3, wx1 = min(W, ((int)cp.xs0[dx1] + TX + 3) & ~3);
           const int wy0 = cp.ys0[dy0], wy1 = min(H, (int)cp.ys0[dy1] + TY);
           tile_load<W>(tile, stride, bfr, wx0, wy0, wx1, wy1, lane);
-          if (dual) tile_load<W>(tile2, stride, bfr2, wx0, wy0, wx1, wy1, lane);
+          if (dual && two_frames) tile_load<W>(tile2, stride, bfr2, wx0, wy0, wx1, wy1, lane);
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
@@ -385,11 +427,13 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
               const int l = __ffs(m) - 1;
               const uint32_t zl = __shfl_sync(0xffffffffu, e.z, l);
               const bool st2 = (zl >> 15) & 1u; /* entry of the second state: its own scratch and record */
+              const bool twice = dual && two_frames && ((zl >> 14) & 1u); /* in both frames: paint it into both windows */
               uint8_t *ts = st2 ? tile2 : tile;
               const uint32_t *Rs = st2 ? R2 : R;
               if (!((zl >> 16) & TBX_ENTRY_PAR)) { /* in-order group: one entry at a time */
                 const uint4 q = list[c * 32 + l];
                 paint_entry_coop(ts, stride, wx0, wy0, wx1, wy1, q, Rs, lane);
+                if (twice) paint_entry_coop(tile2, stride, wx0, wy0, wx1, wy1, q, R2, lane);
                 __syncwarp();
                 m &= m - 1;
                 continue;
@@ -401,21 +445,26 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
               uint32_t smalls = __ballot_sync(0xffffffffu, small);
               if (__popc(smalls) < 3) { smalls = 0; small = false; } /* too few to pay for one-lane loops: the warp paints each */
               uint32_t big = same & ~smalls;
-              if (small)
+              if (small) {
                 paint_tile_lane(ts, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
                                 (int16_t)(e.y >> 16), e.z & 255u);
+                if (twice)
+                  paint_tile_lane(tile2, stride, wx0, wy0, wx1, wy1, (int16_t)(e.x & 0xffffu), (int16_t)(e.x >> 16), (int16_t)(e.y & 0xffffu),
+                                  (int16_t)(e.y >> 16), e.z & 255u);
+              }
               __syncwarp();
               while (big) {
                 const int lb = __ffs(big) - 1;
                 big &= big - 1;
                 const uint4 q = list[c * 32 + lb];
                 paint_entry_coop(ts, stride, wx0, wy0, wx1, wy1, q, Rs, lane);
+                if (twice) paint_entry_coop(tile2, stride, wx0, wy0, wx1, wy1, q, R2, lane);
                 __syncwarp();
               }
               m &= ~same;
             }
           }
-          if (dual) { tile_max(tile, tile2, stride, wx1 - wx0, wy1 - wy0, lane); __syncwarp(); }
+          if (dual && two_frames) { tile_max(tile, tile2, stride, wx1 - wx0, wy1 - wy0, lane); __syncwarp(); }
           tile_resolve<TX, TY>(tile, stride, wx0, wy0, dx0, dx1, dy0, dy1, dw, plan, out, lane);
           __syncwarp(); /* the scratch canvas is overwritten by the next run */
         }
