@@ -58,15 +58,15 @@ def test_area_render_paths_bit_exact(tbx, oracle_mod, game):
 
 @pytest.mark.parametrize("game", GAMES)
 def test_native_render_paths_bit_exact(tbx, oracle_mod, game):
-    """native layouts: broadcast + patch (list, sweep and per-tile rebuild paths) and the canvas kernel"""
+    """native layouts: broadcast + patch with its dense-env hand-over to the canvas kernel (never / always / mixed), and the
+    canvas kernel alone"""
     n = 45
     pool, ref = _advance(tbx, oracle_mod, game, n, 1200 if game == "breakout" else 400, 78)
-    keys = ("TBX_AREA_LCAP", "TBX_NATIVE_KERNEL")
+    keys = ("TBX_NATIVE_KERNEL", "TBX_NATIVE_DENSE")
     try:
         for mode in ("rgb", "rgba", "gray"):
             want = ref.render(mode).reshape(n, -1)
-            for v in ({}, {"TBX_NATIVE_KERNEL": "patch"}, {"TBX_NATIVE_KERNEL": "patch", "TBX_AREA_LCAP": "24"},
-                      {"TBX_NATIVE_KERNEL": "patch", "TBX_AREA_LCAP": "3"}, {"TBX_NATIVE_KERNEL": "canvas"}):
+            for v in ({}, {"TBX_NATIVE_DENSE": "-1"}, {"TBX_NATIVE_DENSE": "0"}, {"TBX_NATIVE_DENSE": "3"}, {"TBX_NATIVE_KERNEL": "canvas"}):
                 for k in keys:
                     os.environ.pop(k, None)
                 os.environ.update(v)

@@ -19,10 +19,12 @@ cap() { # name kernel-regex traffic-key bench-args...
 }
 cap area_brk area_tile breakout/gray84/65536 --game breakout
 cap step_brk step_kernel breakout/step/65536 --game breakout
-cap rgba_brk render_kernel breakout/rgba/65536 --game breakout --obs rgba
+cap fill_brk base_fill breakout/rgba-fill/65536 --game breakout --obs rgba
+cap patch_brk native_patch breakout/rgba-patch/65536 --game breakout --obs rgba
 cap fill_amidar base_fill amidar/rgb-fill/65536 --game amidar --obs rgb
 cap patch_amidar native_patch amidar/rgb-patch/65536 --game amidar --obs rgb
-cap rgb_si render_kernel space_invaders/rgb/65536 --game space_invaders --obs rgb
+cap fill_si base_fill space_invaders/rgb-fill/65536 --game space_invaders --obs rgb
+cap patch_si native_patch space_invaders/rgb-patch/65536 --game space_invaders --obs rgb
 cap area_amidar area_tile amidar/gray84/65536 --game amidar
 cap area_si area_tile space_invaders/gray84/65536 --game space_invaders
 rm -f gpurun_out/${TAG}_prof_*.ncu-rep
@@ -33,12 +35,13 @@ for l in open(sys.argv[1]):
         d=json.loads(l); r=d["roofline"]; print("%s: %.2f M/s render %.3f ms %.0f GB/s frac %.3f step %.3f ms"%(sys.argv[2], d["value"]/1e6, r["launch_ms"], r["achieved"], r["frac"], r["step_kernel_ms"]))
 PY
 }
-for cfg in "breakout rgb" "breakout rgba" "breakout gray" "amidar rgb" "space_invaders rgb" "amidar gray84" "space_invaders gray84"; do
+for cfg in "breakout rgb" "breakout rgba" "breakout gray" "amidar rgb" "amidar gray" "space_invaders rgb" "space_invaders rgba" "space_invaders gray" "amidar gray84" "space_invaders gray84"; do
   set -- $cfg
   timeout 300 python bench.py --game $1 --obs $2 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_$1_$2.log 2>&1; show gpurun_out/${TAG}_bench_$1_$2.log "$1 $2"
 done
 timeout 300 python bench.py --envs 131072 --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_brk_131072.log 2>&1; show gpurun_out/${TAG}_bench_brk_131072.log "breakout gray84 131072 envs"
 timeout 300 python bench.py --policy track --presteps 3000 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_track.log 2>&1; show gpurun_out/${TAG}_bench_track.log "breakout gray84 mid-game"
+timeout 300 python bench.py --obs rgb --policy track --presteps 3000 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_track_rgb.log 2>&1; show gpurun_out/${TAG}_bench_track_rgb.log "breakout rgb mid-game"
 for g in breakout amidar space_invaders; do
   timeout 300 python bench.py --wrapped --game $g --steps 50 --warmup 5 > gpurun_out/${TAG}_bench_wrapped_$g.log 2>&1; tail -1 gpurun_out/${TAG}_bench_wrapped_$g.log | cut -c1-200
 done

@@ -41,6 +41,7 @@ struct tbx_pool {
   std::vector<uint32_t> h_base_rgba[2];
   std::vector<uint8_t> h_base_gray[2];
   std::map<std::pair<int, int>, struct AreaRes> area;
+  int32_t *d_dense; /* [0] = count, [8..] = env ids the patch kernel left to the canvas kernel */
   /* tbx_step_host staging */
   cudaStream_t hs;
   int32_t *h_actions_dev, *h_reward_dev, *h_score_dev, *h_lives_dev;
@@ -106,7 +107,7 @@ int tbx_pool_destroy(tbx_pool *p) {
   if (!p) return TBX_OK;
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
-  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal);
+  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal); cudaFree(p->d_dense);
   drop_render_cache(p);
   cudaFree(p->h_actions_dev); cudaFree(p->h_reward_dev); cudaFree(p->h_score_dev); cudaFree(p->h_lives_dev); cudaFree(p->h_done_dev); cudaFree(p->h_obs_dev);
   if (p->hs) cudaStreamDestroy(p->hs);
@@ -128,7 +129,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
   p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = p->d_base_rgb[0] = p->d_base_rgb[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
-  p->hs = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
+  p->hs = 0; p->d_dense = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
     tbx::default_config(g, p->cfg);
@@ -325,7 +326,7 @@ template <int GAME, int PIX> static int launch_native_pix(const tbx_pool *p, con
   typedef typename Traits<GAME>::Cfg Cfg;
   static int configured = 0;
   const int threads = 256;
-  const int patch_smem = a.smem_canvas + (threads / 32) * a.warp_bytes;
+  const int patch_smem = a.smem_canvas; /* the records of the CTA's 8 envs */
   if (!configured) {
     CK((cudaFuncSetAttribute(base_fill_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)));
     CK((cudaFuncSetAttribute(native_patch_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
@@ -418,6 +419,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.planes2 = dual ? dual->planes2 : 0; a.reset_flags = dual ? dual->reset_flags : 0;
   a.stack_k = dual ? dual->stack_k : 1; a.stack_slot = dual ? dual->stack_slot : 0; a.env_stride = fb * (size_t)a.stack_k; a.tile_bytes = 0;
+  a.dense_list = 0; a.dense_count = 0; a.dense_flag = 0; a.dense_threshold = 0; a.env_list = 0; a.env_count = 0;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h; a.tile_stride = 0; a.warp_bytes = 0; a.list_cap = 0; a.tile_hshift = 0; a.max_run = 0; a.band_rows = 0; a.smem_rects = 0;
   for (int b = 0; b < 2; b++) {
     a.base[b] = pix == 4 ? p->d_base_rgba[b] : pix == 3 ? p->d_base_rgb[b] : p->d_base_gray[b];
@@ -425,6 +427,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   }
   a.smem_canvas = align16(p->info->rec_words * TBX_EPC * 4) * (dual ? 2 : 1);
   int smem_total, tx = 1, ty = 1;
+  bool patch_first = false;
   const TbxAreaPlan *host_plan = 0;
   if (mode == TBX_OBS_GRAY_AREA) {
     AreaRes *ar = 0;
@@ -492,22 +495,13 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
     }
     a.smem_rects = a.smem_canvas + align16(canvas_rows * W + 16);
   } else {
-    /* Two renderers (TBX_NATIVE_KERNEL=patch|canvas overrides): broadcast + patch (tbx_render_native.cuh) wins where few
-     * pixels differ from the base frame (Amidar RGB 22.8 -> 35.3 M frames/s), the canvas kernel below where an env
-     * repaints ~50 sprites (Space Invaders 15.1 vs 10.1) or in mid-game Breakout; Breakout's fresh games are a tie. */
+    /* Default: broadcast + patch (tbx_render_native.cuh) -- the base frame leaves through the TMA engine at HBM speed, what
+     * differs from it is painted straight into the frame.  Envs that differ in many places (a Breakout wall with more
+     * than 24 bricks gone, an Amidar maze with more than 48 painted tiles / boxes; TBX_NATIVE_DENSE overrides) are cheaper
+     * to repaint in shared memory: the patch kernel lists them and the canvas kernel below renders exactly those.
+     * TBX_NATIVE_KERNEL=canvas renders everything with the canvas kernel. */
     const char *ksel = getenv("TBX_NATIVE_KERNEL");
-    const bool patch = ksel ? !strcmp(ksel, "patch") : p->game == TBX_AMIDAR;
-    if (patch && !dual) {
-      int max_rows = (40 * 1024) / (W * pix);
-      if (max_rows < 1) max_rows = 1;
-      const int nb = (H + max_rows - 1) / max_rows;
-      a.band_rows = (H + nb - 1) / nb;
-      a.list_cap = TBX_NT_LCAP;
-      if (const char *env = getenv("TBX_AREA_LCAP")) a.list_cap = atoi(env);
-      if (a.list_cap < 1 || a.list_cap > TBX_NT_LCAP) a.list_cap = TBX_NT_LCAP;
-      a.warp_bytes = align16(TBX_NT_LCAP * 24 + 64 + TBX_NT_MAX_RUN(pix) * TBX_NT_TW * pix * TBX_NT_TH);
-      return launch_native(p, mode, a, align16(a.band_rows * W * pix), (cudaStream_t)stream);
-    }
+    patch_first = !(ksel && !strcmp(ksel, "canvas")) && !dual;
     /* canvas bands of at most ~40 KB so that five CTAs stay resident per SM */
     int max_rows = (40 * 1024) / (W * pix);
     if (max_rows < 1) max_rows = 1;
@@ -515,9 +509,30 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
     a.band_rows = (H + nb - 1) / nb;
     a.smem_rects = a.smem_canvas + align16(a.band_rows * W * pix);
   }
-  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 64 + TBX_MAX_BIG * (int)sizeof(uint4); /* + list counts, per-env base ids, the big-primitive queue */
+  smem_total = a.smem_rects + 2 * TBX_MAX_RECTS * (int)sizeof(int4) + 128 + TBX_MAX_BIG * (int)sizeof(uint4); /* + list counts, per-env base / env ids, the big-primitive queue */
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
+  if (patch_first) {
+    int thr = p->game == TBX_BREAKOUT ? 24 : p->game == TBX_AMIDAR ? 48 : INT32_MAX;
+    if (const char *env = getenv("TBX_NATIVE_DENSE")) thr = atoi(env) < 0 ? INT32_MAX : atoi(env);
+    RenderArgs f = a; /* same bands for the broadcast */
+    if (thr != INT32_MAX) {
+      if (!p->d_dense) CK(cudaMalloc(&p->d_dense, ((size_t)p->n_pad + 8) * sizeof(int32_t) + (size_t)p->n_pad));
+      f.dense_list = p->d_dense + 8;
+      f.dense_count = p->d_dense;
+      f.dense_flag = reinterpret_cast<uint8_t *>(p->d_dense + 8 + p->n_pad);
+      f.dense_threshold = thr;
+      CK(cudaMemsetAsync(p->d_dense, 0, sizeof(int32_t), s));
+      if (p->game == TBX_BREAKOUT) dense_classify_kernel<TBX_BREAKOUT><<<blocks(p->n, 8), 256, 0, s>>>(f, p->cfg.brk);
+      else if (p->game == TBX_AMIDAR) dense_classify_kernel<TBX_AMIDAR><<<blocks(p->n, 8), 256, 0, s>>>(f, p->cfg.ami);
+      else dense_classify_kernel<TBX_SPACE_INVADERS><<<blocks(p->n, 8), 256, 0, s>>>(f, p->cfg.si);
+      CK(cudaGetLastError());
+    }
+    r = launch_native(p, mode, f, align16(a.band_rows * W * pix), s);
+    if (r || thr == INT32_MAX) return r;
+    a.env_list = p->d_dense + 8;
+    a.env_count = p->d_dense;
+  }
   if (p->game == TBX_BREAKOUT) return launch_render_mode<TBX_BREAKOUT>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
   if (p->game == TBX_AMIDAR) return launch_render_mode<TBX_AMIDAR>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);
   return launch_render_mode<TBX_SPACE_INVADERS>(mode, tx, ty, a, cfg_ptr(p), host_plan, smem_total, s);

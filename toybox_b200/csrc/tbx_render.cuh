@@ -52,6 +52,15 @@ template <> struct Traits<TBX_BREAKOUT> {
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return brk_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int base, int &b, int &e, int &mode) { brk_group(g, R, t, base, b, e, mode); }
   static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
+  /* cheap estimate of the number of entries that differ from the base frame: the dead bricks */
+  template <class LD> static __device__ __forceinline__ int dense_hint(LD ld, const Cfg &c, const Table *t) { /* ld(w) = word w of the env */
+    const int tbl = (int32_t)ld(TBX_W(TbxHdr, tbl));
+    const Table &T = t[tbl];
+    if (!(tbl == c.default_tbl && T.delta_ok)) return 1 << 20; /* not on base frame 1: every brick is an entry */
+    int n = 0;
+    for (int k = 0; k < 5; k++) n += __popc(T.all_mask[k] & ~ld(TBX_W(BrkRec, alive) + k));
+    return n;
+  }
 };
 template <> struct Traits<TBX_SPACE_INVADERS> {
   typedef SiCfg Cfg; typedef int Table; typedef SiRec Rec;
@@ -62,6 +71,7 @@ template <> struct Traits<TBX_SPACE_INVADERS> {
   static __device__ __forceinline__ int base_id(const uint32_t *, const Cfg &, const Table *) { return 0; }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
   static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
+  template <class LD> static __device__ __forceinline__ int dense_hint(LD, const Cfg &, const Table *) { return 0; } /* ~50 sprites, always: painted once each */
 };
 template <> struct Traits<TBX_AMIDAR> {
   typedef AmiCfg Cfg; typedef AmiTable Table; typedef AmiRec Rec;
@@ -86,6 +96,16 @@ template <> struct Traits<TBX_AMIDAR> {
     b = AMI_SLOT_TILES + 32 * (__ffs(m) - 1);
     e = AMI_SLOT_TILES + 32 * (32 - __clz(m));
   }
+  /* warp-cooperative (every lane calls it): tiles whose packed tag differs from the config board + painted boxes */
+  template <class LD> static __device__ __forceinline__ int dense_hint(LD ld, const Cfg &c, const Table *) {
+    const int lane = threadIdx.x & 31;
+    int n = 0;
+    if (lane < TBX_AMI_BH) {
+      const uint32_t d0 = ld(AMI_W(tiles) + 2 * lane) ^ c.board[lane][0], d1 = ld(AMI_W(tiles) + 2 * lane + 1) ^ c.board[lane][1];
+      n = __popc((d0 | (d0 >> 1)) & 0x55555555u) + __popc((d1 | (d1 >> 1)) & 0x55555555u);
+    }
+    return __reduce_add_sync(0xffffffffu, n) + __popc(ld(AMI_W(box_painted)));
+  }
 };
 
 struct RenderArgs {
@@ -106,6 +126,15 @@ struct RenderArgs {
   const uint8_t *reset_flags;
   size_t env_stride; /* bytes between the observations of consecutive envs (frame_bytes * stack_k) */
   int stack_k, stack_slot, tile_bytes;
+  /* native layouts, broadcast + patch (tbx_render_native.cuh): envs with more than dense_threshold entries (by the
+   * game's cheap estimate) are not patched but appended to dense_list; the canvas kernel then repaints exactly those
+   * (env_list / env_count != NULL: CTA b renders envs env_list[8b .. 8b+7], b < ceil(*env_count / 8)) */
+  int32_t *dense_list;
+  int *dense_count;
+  uint8_t *dense_flag; /* [n]: 1 = left to the canvas kernel (written by dense_classify_kernel) */
+  int dense_threshold;
+  const int32_t *env_list;
+  const int *env_count;
   int tile_stride, warp_bytes, list_cap, tile_hshift, max_run; /* INTER_AREA tile kernel (tbx_render_area.cuh): scratch row pitch, shared memory per warp */
 };
 
@@ -356,18 +385,22 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
   int4 *rect_buf = reinterpret_cast<int4 *>(smem + a.smem_rects); /* two lists, used alternately */
   int *rect_n = reinterpret_cast<int *>(rect_buf + 2 * TBX_MAX_RECTS);
   int *env_base = rect_n + 2; /* base frame id of each env of the chunk */
-  int *n_big = env_base + TBX_EPC;
-  uint4 *big_buf = reinterpret_cast<uint4 *>(rect_n + 16);
+  int *n_big = env_base + 2 * TBX_EPC;
+  uint4 *big_buf = reinterpret_cast<uint4 *>(rect_n + 32);
   const typename T::Cfg &cfg = cfg_c;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int e0 = blockIdx.x * TBX_EPC;
-  const int ne = min(TBX_EPC, a.n - e0);
+  const int ne = min(TBX_EPC, (a.env_count ? *a.env_count : a.n) - e0);
+  if (ne <= 0) return; /* env-list mode: nothing (left) to repaint */
+  int *env_id = env_base + TBX_EPC; /* the env each slot of the chunk renders */
+  if (tid < TBX_EPC) env_id[tid] = a.env_list ? (tid < ne ? a.env_list[e0 + tid] : 0) : e0 + tid;
+  __syncthreads();
 
   /* coalesced load of the chunk's state words: thread -> (word, env) with env fastest */
   for (int i = tid; i < RW * TBX_EPC; i += TBX_NT) {
     int w = i / TBX_EPC, j = i - w * TBX_EPC;
-    if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
+    if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + env_id[j]];
   }
   if (tid < 2) rect_n[tid] = 0;
   if (tid == 2) *n_big = 0;
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
       const int align = (int)(a.frame_bytes | (size_t)b0 | (size_t)b1);
       for (int j = 0; j < ne; j++) {
         const uint8_t *src = env_base[j] ? a.base_out[1] : a.base_out[0];
-        uint8_t *dst = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+        uint8_t *dst = a.dst + (size_t)env_id[j] * a.frame_bytes;
         if ((align & 15) == 0) {
           for (int i = (b0 >> 4) + tid; i < (b1 >> 4); i += TBX_NT) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
         } else if ((align & 3) == 0) {
@@ -417,7 +450,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
        * (the barriers above order these byte stores after the band's base copy).  Lanes own output columns (their
        * taps stay in registers), warps own output rows; narrow rectangles pack several rows into one warp.
        * Straight-line TX x TY taps, surplus taps carry zero weights (x + 0*b == x for these sums). */
-      uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+      uint8_t *out = a.dst + (size_t)env_id[j] * a.frame_bytes;
       int nr = *n_rects;
       const bool overflow = nr > TBX_MAX_RECTS;
       if (overflow) nr = 1;
@@ -473,7 +506,7 @@ __global__ void __launch_bounds__(TBX_RENDER_MAX_THREADS, TBX_RENDER_MIN_CTAS) r
     const int base = env_base[j];
     int4 *rects = rect_buf + (j & 1) * TBX_MAX_RECTS;
     int *n_rects = rect_n + (j & 1);
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.frame_bytes;
+    uint8_t *out = a.dst + (size_t)env_id[j] * a.frame_bytes;
     if (canvas_base != base) load_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1);
     else restore_canvas<PIX, W>(canvas, (base ? a.base[1] : a.base[0]), r0, r1, rect_buf + ((j - 1) & 1) * TBX_MAX_RECTS, rect_n[(j - 1) & 1]);
     canvas_base = base;
