@@ -56,3 +56,30 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|oracle/|oracle\.py|tbo\.h", text, flags=re.M), (dirpath, f)
                 assert "libtbo" not in text and "tbo_" not in text, (dirpath, f)
+
+
+def test_field_lookup_is_host_only_and_matches_the_record_layout():
+    """tbx_field_lookup needs no GPU: property paths of the JSON state schema -> (word, kind, bit)"""
+    import ctypes as C
+    from toybox_b200 import _lib
+    L = _lib.lib()
+
+    def look(game, path):
+        w, k, b = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+        rc = L.tbx_field_lookup(game.encode(), path.encode(), C.byref(w), C.byref(k), C.byref(b))
+        return rc, w.value, k.value, b.value
+
+    # header words: rand[2] u64, sim_rand[2] u64 = words 0..7, then lives, score, level
+    for game in ("breakout", "amidar", "space_invaders"):
+        assert look(game, "lives")[:3] == (0, 8, 0) and look(game, "score")[:3] == (0, 9, 0) and look(game, "level")[:3] == (0, 10, 0)
+    rc, w, k, b = look("breakout", "paddle.position.x")
+    assert rc == 0 and w == 16 and k == 1                      # the first f64 after the 16-word header
+    assert look("breakout", "paddle.velocity.y")[1] == 16 + 6
+    rc, w0, k, b0 = look("breakout", "bricks[0].alive")
+    rc, w37, k, b37 = look("breakout", "bricks[37].alive")
+    assert k == 3 and b0 == 0 and w37 == w0 + 1 and b37 == 5   # bit 37 = word 1, bit 5 of the alive mask
+    assert look("space_invaders", "ufo.appearance_counter")[2] == 4 and look("amidar", "board.boxes[28].painted")[2:] == (3, 28)
+    assert look("amidar", "enemies[1].position.y")[1] - look("amidar", "enemies[0].position.y")[1] == 31   # AmiMob = 31 words
+    for game, path in (("breakout", "no.such"), ("breakout", "balls[9].position.x"), ("amidar", "ship.x"), ("pong", "lives")):
+        assert look(game, path)[0] != 0
+        assert b"" != L.tbx_last_error()
