@@ -8,7 +8,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 GAMES = ["breakout", "amidar", "space_invaders"]
-VARIANTS = [{}, {"TBX_AREA_LCAP": "24"}, {"TBX_AREA_LCAP": "3"}, {"TBX_AREA_KERNEL": "cta"}, {"TBX_AREA_THREADS": "128"},
+VARIANTS = [{}, {"TBX_AREA_DIGIT_CACHE": "0"}, {"TBX_AREA_LCAP": "24"}, {"TBX_AREA_LCAP": "3"}, {"TBX_AREA_KERNEL": "cta"}, {"TBX_AREA_THREADS": "128"},
             {"TBX_AREA_TILE_H": "4", "TBX_AREA_MAX_RUN": "8"}, {"TBX_AREA_TILE_H": "16"}, {"TBX_AREA_MAX_RUN": "1", "TBX_AREA_LCAP": "40"}]
 SIZES = [(84, 84), (96, 80), (64, 64), (48, 60), (100, 37)]
 
@@ -34,7 +34,7 @@ def _advance(tbx, oracle_mod, game, n, steps, seed):
 
 
 def _set_env(v):
-    for k in ("TBX_AREA_LCAP", "TBX_AREA_KERNEL", "TBX_AREA_THREADS", "TBX_AREA_TILE_H", "TBX_AREA_MAX_RUN"):
+    for k in ("TBX_AREA_LCAP", "TBX_AREA_KERNEL", "TBX_AREA_THREADS", "TBX_AREA_TILE_H", "TBX_AREA_MAX_RUN", "TBX_AREA_DIGIT_CACHE"):
         os.environ.pop(k, None)
     os.environ.update(v)
 
@@ -76,4 +76,40 @@ def test_native_render_paths_bit_exact(tbx, oracle_mod, game):
     finally:
         for k in keys:
             os.environ.pop(k, None)
+        pool.close()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_hud_digit_patches_every_value(tbx, oracle_mod, game):
+    """pre-resolved HUD digit patches: every digit value in every decimal position (isolated single digits use the
+    patch, multi-digit numbers fall back to the tiles), on fresh and on advanced games, several output sizes"""
+    n = 64
+    pool, ref = _advance(tbx, oracle_mod, game, n, 120, 90)
+    scores = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 19, 70, 100, 305, 999, 1000, 4821, 90909, 123456, 7654321, 10 ** 9] * 3
+    scores = np.asarray(scores[:n], np.int64)
+    lives = 1 + (np.arange(n) % 9)
+    try:
+        pool.set_property("score", scores.astype(np.int32))
+        pool.set_property("lives", lives.astype(np.int32))
+        if game == "amidar":
+            pool.set_property("jumps", (np.arange(n) % 10).astype(np.int32))
+        if game == "space_invaders":
+            pool.set_property("life_display_timer", (np.arange(n) % 2) * 30)
+        for i in range(n):
+            js = ref.state_json(i)
+            js["score"] = int(scores[i]); js["lives"] = int(lives[i])
+            if game == "amidar":
+                js["jumps"] = int(i % 10)
+            if game == "space_invaders":
+                js["life_display_timer"] = int((i % 2) * 30)
+            ref.write_state_json(i, js)
+        for ow, oh in ((84, 84), (96, 80), (64, 64)):
+            want = ref.render("gray84", ow, oh).reshape(n, -1)
+            for v in ({}, {"TBX_AREA_DIGIT_CACHE": "0"}):
+                _set_env(v)
+                got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
+                bad = np.argwhere(got != want)
+                assert bad.size == 0, (game, ow, oh, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+    finally:
+        _set_env({})
         pool.close()

@@ -879,5 +879,56 @@ void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out) {
   for (int y = 0; y < H; y++) for (int dx = 0; dx < dw; dx++) buf[(size_t)y * dw + dx] = tbx_area_h(gray + (size_t)y * W, t.x, dx);
   for (int dy = 0; dy < dh; dy++) for (int dx = 0; dx < dw; dx++) out[dy * dw + dx] = tbx_area_v(buf.data(), dw, 0, t.y, dy, dx);
 }
+int digit_slot0(int game) { return game == TBX_BREAKOUT ? BRK_SLOT_SCORE : game == TBX_AMIDAR ? AMI_SLOT_SCORE : SI_SLOT_SCORE; }
+int digit_slots(int game) { return game == TBX_BREAKOUT ? BRK_SLOT_BRICKS - BRK_SLOT_SCORE : game == TBX_AMIDAR ? AMI_N_SLOTS - AMI_SLOT_SCORE : SI_SLOT_SHIELDS - SI_SLOT_SCORE; }
+/* one output pixel of cv2's INTER_AREA, the arithmetic of area_resize above (tbx_area_h per tap row, accumulated like tbx_area_v) */
+static uint8_t area_pixel(const uint8_t *gray, int W, const ResizeTab &t, int dx, int dy) {
+  int k = t.y.start[dy], k1 = t.y.start[dy + 1];
+  float s = tbx_fmul(t.y.alpha[k], tbx_area_h(gray + (size_t)t.y.si[k] * W, t.x, dx));
+  for (k++; k < k1; k++) s = tbx_fadd(s, tbx_fmul(t.y.alpha[k], tbx_area_h(gray + (size_t)t.y.si[k] * W, t.x, dx)));
+  int v = tbx_f2i_rn(s);
+  return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+}
+void build_digit_patches(const Config &c, const BrkTable *brk_default, const ResizeTab &t, const TbxAreaPlan &plan, const uint8_t *base_gray,
+                         TbxDigitPatch *out) {
+  const GameInfo *gi = game_info(c.game);
+  const int W = gi->width, H = gi->height;
+  std::vector<uint8_t> gray(base_gray, base_gray + (size_t)W * H);
+  std::vector<uint32_t> rec(gi->rec_words, 0);
+  memset(out, 0, sizeof(TbxDigitPatch) * TBX_DP_SLOTS * 10);
+  const int s0 = digit_slot0(c.game), ns = digit_slots(c.game);
+  for (int idx = 0; idx < ns && idx < TBX_DP_SLOTS; idx++) {
+    const int k = idx % TBX_MAX_DIGITS; /* decimal position inside its field */
+    for (int d = 0; d < 10; d++) {
+      /* a field value whose digit at position k is d (and that shows position k at all) */
+      long long v = d;
+      for (int i = 0; i < k; i++) v *= 10;
+      if (d == 0 && k > 0) { v = 1; for (int i = 0; i <= k; i++) v *= 10; }
+      if (v > 2000000000LL) continue;
+      std::fill(rec.begin(), rec.end(), 0u);
+      TbxHdr &h = *reinterpret_cast<TbxHdr *>(rec.data());
+      h.score = (int32_t)v; h.lives = (int32_t)v;
+      TbxPrim p;
+      if (c.game == TBX_BREAKOUT) p = brk_prim(rec.data(), c.brk, brk_default, s0 + idx);
+      else if (c.game == TBX_AMIDAR) { reinterpret_cast<AmiRec *>(rec.data())->jumps = (int32_t)v; p = ami_prim(rec.data(), c.ami, 0, s0 + idx); }
+      else { reinterpret_cast<SiRec *>(rec.data())->life_display_timer = 1; p = si_prim(rec.data(), s0 + idx); }
+      if (p.h <= 0 || p.bw != 3 || p.off != TBX_BANK_FONT + 5 * d) continue; /* not a digit sprite of this value */
+      const int x0 = p.x < 0 ? 0 : p.x, x1 = p.x + p.w > W ? W : p.x + p.w, y0 = p.y < 0 ? 0 : p.y, y1 = p.y + p.h > H ? H : p.y + p.h;
+      if (x0 >= x1 || y0 >= y1) continue;
+      const int dx0 = plan.xdlo[x0], dx1 = plan.xdhi[x1 - 1], dy0 = plan.ydlo[y0], dy1 = plan.ydhi[y1 - 1];
+      const int w = dx1 - dx0 + 1, hh = dy1 - dy0 + 1;
+      if (w < 1 || hh < 1 || w > 8 || w * hh > TBX_DP_MAX) continue;
+      const uint8_t lum = (uint8_t)tbx_luma(p.color);
+      for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++)
+          if (tbx_prim_covers(p, HOST_BANK, rec.data(), x, y)) gray[(size_t)y * W + x] = lum;
+      TbxDigitPatch &P = out[idx * 10 + d];
+      P.x0 = (uint8_t)dx0; P.y0 = (uint8_t)dy0; P.w = (uint8_t)w; P.h = (uint8_t)hh;
+      for (int r = 0; r < hh; r++)
+        for (int cc = 0; cc < w; cc++) P.px[r * w + cc] = area_pixel(gray.data(), W, t, dx0 + cc, dy0 + r);
+      for (int y = y0; y < y1; y++) memcpy(&gray[(size_t)y * W + x0], base_gray + (size_t)y * W + x0, (size_t)(x1 - x0));
+    }
+  }
+}
 
 } /* namespace tbx */

@@ -78,6 +78,11 @@ void brk_mark_delta_ok(const Config &c, BrkTable &t);
 /* gray bytes of an RGBA frame, and its INTER_AREA down-sample (same arithmetic as the kernels) */
 void frame_to_gray(const uint32_t *rgba, int npix, uint8_t *gray);
 void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out);
+/* the TBX_DP_SLOTS x 10 digit patches of base frame `base_id` (gray) for one output size; out[slot * 10 + digit] */
+void build_digit_patches(const Config &c, const BrkTable *brk_default, const ResizeTab &t, const TbxAreaPlan &plan, const uint8_t *base_gray,
+                         TbxDigitPatch *out);
+int digit_slot0(int game);   /* first draw-list slot of the HUD digit fields */
+int digit_slots(int game);   /* how many consecutive digit slots follow */
 
 } /* namespace tbx */
 #endif

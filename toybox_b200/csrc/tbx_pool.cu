@@ -20,7 +20,7 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct AreaRes { TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; int dw, dh, tx, ty; };
+struct AreaRes { TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; TbxDigitPatch *d_patches[2]; int dw, dh, tx, ty; };
 static void drop_render_cache(struct tbx_pool *p);
 
 struct tbx_pool {
@@ -251,7 +251,7 @@ int tbx_check(tbx_pool *p, void *stream) {
 /* ---- render */
 static void drop_render_cache(tbx_pool *p) {
   for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); cudaFree(p->d_base_rgb[b]); p->d_base_gray[b] = p->d_base_rgba[b] = p->d_base_rgb[b] = 0; }
-  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); }
+  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); cudaFree(kv.second.d_patches[0]); cudaFree(kv.second.d_patches[1]); }
   p->area.clear();
 }
 /* base frames 0/1 of the current config (see tbx_render.cuh), gray and RGBA, on the device */
@@ -286,7 +286,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     if (!tbx::build_area_plan(rs, plan)) return set_err(TBX_EINVAL, "resize: the fused kernel supports destinations up to 128x128 with at most 8 taps per axis");
     AreaRes r;
     r.plan = plan;
-    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0;
+    r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0; r.d_patches[0] = r.d_patches[1] = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; b++) {
@@ -294,6 +294,10 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
       tbx::area_resize(p->h_base_gray[b].data(), rs, base_out.data());
       CK(cudaMalloc(&r.d_base_out[b], base_out.size()));
       CK(cudaMemcpy(r.d_base_out[b], base_out.data(), base_out.size(), cudaMemcpyHostToDevice));
+      std::vector<TbxDigitPatch> patches((size_t)TBX_DP_SLOTS * 10);
+      tbx::build_digit_patches(p->cfg, p->game == TBX_BREAKOUT ? &p->brk_tables[p->cfg.brk.default_tbl] : 0, rs, plan, p->h_base_gray[b].data(), patches.data());
+      CK(cudaMalloc(&r.d_patches[b], patches.size() * sizeof(TbxDigitPatch)));
+      CK(cudaMemcpy(r.d_patches[b], patches.data(), patches.size() * sizeof(TbxDigitPatch), cudaMemcpyHostToDevice));
     }
     it = p->area.insert(std::make_pair(key, r)).first;
   }
@@ -419,7 +423,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.planes2 = dual ? dual->planes2 : 0; a.reset_flags = dual ? dual->reset_flags : 0;
   a.stack_k = dual ? dual->stack_k : 1; a.stack_slot = dual ? dual->stack_slot : 0; a.env_stride = fb * (size_t)a.stack_k; a.tile_bytes = 0;
-  a.dense_list = 0; a.dense_count = 0; a.dense_flag = 0; a.dense_threshold = 0; a.env_list = 0; a.env_count = 0;
+  a.patches[0] = a.patches[1] = 0; a.dense_list = 0; a.dense_count = 0; a.dense_flag = 0; a.dense_threshold = 0; a.env_list = 0; a.env_count = 0;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h; a.tile_stride = 0; a.warp_bytes = 0; a.list_cap = 0; a.tile_hshift = 0; a.max_run = 0; a.band_rows = 0; a.smem_rects = 0;
   for (int b = 0; b < 2; b++) {
     a.base[b] = pix == 4 ? p->d_base_rgba[b] : pix == 3 ? p->d_base_rgb[b] : p->d_base_gray[b];
@@ -434,6 +438,11 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
     r = ensure_area(p, out_w, out_h, &ar);
     if (r) return r;
     a.base_out[0] = ar->d_base_out[0]; a.base_out[1] = ar->d_base_out[1]; a.plan = ar->d_plan;
+    {
+      const char *env = getenv("TBX_AREA_DIGIT_CACHE");
+      const bool on = !(env && atoi(env) == 0);
+      a.patches[0] = on ? ar->d_patches[0] : 0; a.patches[1] = on ? ar->d_patches[1] : 0;
+    }
     tx = ar->tx; ty = ar->ty;
     host_plan = &ar->plan;
     /* Bands of output rows: each (chunk, band) CTA keeps only the canvas rows that feed its output rows, which

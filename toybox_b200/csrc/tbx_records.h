@@ -205,6 +205,12 @@ typedef struct {
   uint8_t ydlo[TBX_AREA_MAX_SRC], ydhi[TBX_AREA_MAX_SRC];
 } TbxAreaPlan;
 
+/* Pre-resolved output patch of ONE HUD digit on the base frame (tbx_render_area.cuh): the bytes of output rectangle
+ * [x0, x0+w) x [y0, y0+h) when the digit sprite is the only thing that differs from the base there.  w == 0: none. */
+#define TBX_DP_MAX 128
+#define TBX_DP_SLOTS 32 /* digit slots per game (score / lives / jumps fields, 10 slots each) */
+typedef struct { uint8_t x0, y0, w, h; uint8_t px[TBX_DP_MAX]; } TbxDigitPatch;
+
 #define TBX_WORDS(T) ((int)(sizeof(T) / 4))
 #define TBX_W(T, field) ((int)(offsetof(T, field) / 4))
 

@@ -52,6 +52,7 @@ template <> struct Traits<TBX_BREAKOUT> {
   static __device__ __forceinline__ int base_id(const uint32_t *R, const Cfg &c, const Table *t) { return brk_base_id(R, c, t); }
   static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int base, int &b, int &e, int &mode) { brk_group(g, R, t, base, b, e, mode); }
   static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
+  static __device__ __forceinline__ int digit_index(int s) { return s >= BRK_SLOT_SCORE && s < BRK_SLOT_BRICKS ? s - BRK_SLOT_SCORE : -1; } /* HUD digit slots */
   /* cheap estimate of the number of entries that differ from the base frame: the dead bricks */
   template <class LD> static __device__ __forceinline__ int dense_hint(LD ld, const Cfg &c, const Table *t) { /* ld(w) = word w of the env */
     const int tbl = (int32_t)ld(TBX_W(TbxHdr, tbl));
@@ -71,6 +72,7 @@ template <> struct Traits<TBX_SPACE_INVADERS> {
   static __device__ __forceinline__ int base_id(const uint32_t *, const Cfg &, const Table *) { return 0; }
   static __device__ __forceinline__ void group(int g, const uint32_t *, const Table *, int, int &b, int &e, int &mode) { si_group(g, b, e, mode); }
   static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
+  static __device__ __forceinline__ int digit_index(int s) { return s >= SI_SLOT_SCORE && s < SI_SLOT_SHIELDS ? s - SI_SLOT_SCORE : -1; }
   template <class LD> static __device__ __forceinline__ int dense_hint(LD, const Cfg &, const Table *) { return 0; } /* ~50 sprites, always: painted once each */
 };
 template <> struct Traits<TBX_AMIDAR> {
@@ -96,6 +98,7 @@ template <> struct Traits<TBX_AMIDAR> {
     b = AMI_SLOT_TILES + 32 * (__ffs(m) - 1);
     e = AMI_SLOT_TILES + 32 * (32 - __clz(m));
   }
+  static __device__ __forceinline__ int digit_index(int s) { return s >= AMI_SLOT_SCORE && s < AMI_N_SLOTS ? s - AMI_SLOT_SCORE : -1; }
   /* warp-cooperative (every lane calls it): tiles whose packed tag differs from the config board + painted boxes */
   template <class LD> static __device__ __forceinline__ int dense_hint(LD ld, const Cfg &c, const Table *) {
     const int lane = threadIdx.x & 31;
@@ -135,6 +138,7 @@ struct RenderArgs {
   int dense_threshold;
   const int32_t *env_list;
   const int *env_count;
+  const TbxDigitPatch *patches[2]; /* INTER_AREA: pre-resolved HUD digit patches per base frame, [slot * 10 + digit]; NULL = off */
   int tile_stride, warp_bytes, list_cap, tile_hshift, max_run; /* INTER_AREA tile kernel (tbx_render_area.cuh): scratch row pitch, shared memory per warp */
 };
 

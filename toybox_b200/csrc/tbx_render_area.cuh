@@ -71,6 +71,7 @@ __device__ __forceinline__ void paint_tile(uint8_t *tile, int stride, int wx0, i
  *        ENTRY_SMALL = solid rectangle of at most 128 pixels (one lane can paint it alone). */
 #define TBX_ENTRY_PAR 1u
 #define TBX_ENTRY_SMALL 2u
+#define TBX_ENTRY_DIGIT 4u /* HUD digit with a pre-resolved patch candidate: z bits 24..29 = digit slot index */
 template <int W>
 __device__ __forceinline__ bool make_entry(const TbxPrim &p, int g, int gmode, int rA, int rB, int dyA, int dyB, const TbxAreaPlan *__restrict__ plan,
                                            uint4 &e, uint32_t &ext) { /* g: group index | 0x80 for the second state of dual mode */
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       __syncwarp();
       int n = 0;
       bool overflow = false;
+      const bool use_patches = !dual && a.patches[0] != 0 && nsw == 1; /* whole frame in one sweep: a digit's footprint is not clipped */
       if constexpr (!dual) {
         for (int g = 0; g < T::NG && !overflow; g++) {
           int gb, ge, gmode;
@@ -312,9 +314,12 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
             if (n + __popc(m) > a.list_cap) { overflow = true; break; }
             if (ok) {
               const int slot = n + __popc(m & lt_mask);
+              const int didx = T::digit_index(s);
+              const bool cand = use_patches && didx >= 0 && p.bw == 3 && p.off < TBX_BANK_FONT + 50; /* a font sprite in a HUD digit slot */
+              if (cand) e.z |= (TBX_ENTRY_DIGIT << 16) | ((uint32_t)didx << 24);
               list[slot] = e;
               exts[slot] = ext;
-              mark_tiles(tmask, ext, ths);
+              if (!cand) mark_tiles(tmask, ext, ths); /* candidates are marked below unless their patch can be used */
             }
             n += __popc(m);
           }
@@ -372,6 +377,48 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       if (overflow) {
         tile_row_rebuild<GAME, TX, TY>(R, R2, cfg, tables, base, base2, bfr, bfr2, plan, cp, tile, tile2, stride, tyA, ths, rA, rB, dyA, dyB, out, lane);
         continue;
+      }
+      /* 2b. HUD digits: a digit entry whose output rectangle meets no other entry's is the only thing that differs from
+       * the base there, so its pre-resolved patch (host-built per slot and digit value, tbx_host.cpp) IS the result:
+       * the entry leaves the list and the patch is copied after the tiles.  Others are marked like any entry. */
+      uint32_t iso[TBX_TILE_LCAP / 32];
+#pragma unroll
+      for (int c = 0; c < TBX_TILE_LCAP / 32; c++) iso[c] = 0;
+      if (use_patches) {
+        const TbxDigitPatch *__restrict__ patches = base ? a.patches[1] : a.patches[0];
+#pragma unroll
+        for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
+          if (c * 32 >= n) continue;
+          const int i0 = c * 32 + lane;
+          const bool cand = i0 < n && ((list[i0 < n ? i0 : 0].z >> 16) & TBX_ENTRY_DIGIT);
+          unsigned candm = __ballot_sync(0xffffffffu, cand);
+          if (n > 48) { /* a crowded frame (a wall full of holes): not worth the pairwise tests, mark the digits like any entry */
+            if (cand) mark_tiles(tmask, exts[i0], ths);
+            candm = 0;
+          }
+          while (candm) {
+            const int l = __ffs(candm) - 1;
+            candm &= candm - 1;
+            const int i = c * 32 + l;
+            const uint32_t xi = exts[i];
+            const int xlo = xi & 255u, xhi = (xi >> 8) & 255u, ylo = (xi >> 16) & 255u, yhi = xi >> 24;
+            bool ov = false;
+            for (int j = lane; j < n; j += 32) {
+              const uint32_t xj = exts[j];
+              ov |= j != i && (int)(xj & 255u) <= xhi && (int)((xj >> 8) & 255u) >= xlo && (int)((xj >> 16) & 255u) <= yhi && (int)(xj >> 24) >= ylo;
+            }
+            const uint4 ei = list[i];
+            const TbxDigitPatch *P = patches + ((ei.z >> 24) & 63u) * 10 + (ei.w & 0xffffu) / 5u;
+            const bool usable = !__any_sync(0xffffffffu, ov) && __ldg(&P->w) != 0;
+            if (usable) iso[c] |= 1u << l;
+            else if (lane == 0) mark_tiles(tmask, xi, ths);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < TBX_TILE_LCAP / 32; c++)
+          if ((iso[c] >> lane) & 1u) exts[c * 32 + lane] = 0x000000ffu; /* never hit: the tiles ignore it */
+        __syncwarp();
       }
       if (redo_all) { /* every tile of the sweep, whether an entry touches it or not */
         __syncwarp();
@@ -467,6 +514,24 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
           if (dual && two_frames) { tile_max(tile, tile2, stride, wx1 - wx0, wy1 - wy0, lane); __syncwarp(); }
           tile_resolve<TX, TY>(tile, stride, wx0, wy0, dx0, dx1, dy0, dy1, dw, plan, out, lane);
           __syncwarp(); /* the scratch canvas is overwritten by the next run */
+        }
+      }
+      if (use_patches) { /* the isolated digits: their patches go in last (a run's bounding box may have swept over them) */
+        const TbxDigitPatch *__restrict__ patches = base ? a.patches[1] : a.patches[0];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < TBX_TILE_LCAP / 32; c++) {
+          uint32_t m = iso[c];
+          while (m) {
+            const int i = c * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const uint4 ei = list[i];
+            const TbxDigitPatch *P = patches + ((ei.z >> 24) & 63u) * 10 + (ei.w & 0xffffu) / 5u;
+            const int px0 = __ldg(&P->x0), py0 = __ldg(&P->y0), pw = __ldg(&P->w), ph = __ldg(&P->h);
+            const int cc = lane & 7;
+            if (cc < pw)
+              for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = __ldg(&P->px[r * pw + cc]);
+          }
         }
       }
     }
