@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       __syncwarp();
       int n = 0;
       bool overflow = false;
-      const bool use_patches = !dual && a.patches[0] != 0 && nsw == 1; /* whole frame in one sweep: a digit's footprint is not clipped */
+      /* whole frame in one sweep: a digit's footprint is not clipped; dual mode: both frames on the same base frame */
+      const bool use_patches = a.patches[0] != 0 && nsw == 1 && (!dual || base == base2);
       if constexpr (!dual) {
         for (int g = 0; g < T::NG && !overflow; g++) {
           int gb, ge, gmode;
@@ -353,10 +354,16 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
             if (n + __popc(m1) + __popc(m2) > a.list_cap) { overflow = true; break; }
             const int slot = n + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
             if (okA) {
-              if (both) eA.z |= 0x40u << 8;
+              bool cand = false;
+              if (both) {
+                eA.z |= 0x40u << 8;
+                const int didx = T::digit_index(s); /* the same HUD digit in both frames: a patch candidate (2b) */
+                cand = use_patches && didx >= 0 && pA.bw == 3 && pA.off < TBX_BANK_FONT + 50;
+                if (cand) eA.z |= (TBX_ENTRY_DIGIT << 16) | ((uint32_t)didx << 24);
+              }
               list[slot] = eA;
               exts[slot] = xA;
-              mark_tiles(tmask, xA, ths);
+              if (!cand) mark_tiles(tmask, xA, ths);
             }
             if (okB && !both) {
               list[slot + (okA ? 1 : 0)] = eB;
