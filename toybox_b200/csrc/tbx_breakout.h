@@ -270,12 +270,21 @@ TBX_HD int brk_base_id(const uint32_t *R, const BrkCfg &c, const BrkTable *table
   int t = (int32_t)R[TBX_HW(tbl)];
   return (t == c.default_tbl && tables[t].delta_ok) ? 1 : 0;
 }
+TBX_HD bool brk_alive_bit(const uint32_t *R, int i) { return (R[BRK_W(alive) + (i >> 5)] >> (i & 31)) & 1u; }
+/* brick b sits directly below brick a: same columns, a's bottom edge is b's top edge */
+TBX_HD bool brk_stacked(const BrkTable &T, int a, int b) { return T.ix[a] == T.ix[b] && T.iw[a] == T.iw[b] && T.iy[a] + T.ih[a] == T.iy[b]; }
 TBX_HD TbxPrim brk_prim_delta(const uint32_t *R, const BrkCfg &c, const BrkTable *tables, int slot, int base) {
   if (base == 1 && slot >= BRK_SLOT_BRICKS && slot < BRK_SLOT_PADDLE) {
     int i = slot - BRK_SLOT_BRICKS;
     const BrkTable &T = tables[(int32_t)R[TBX_HW(tbl)]];
-    if (i >= T.n_bricks || ((R[BRK_W(alive) + (i >> 5)] >> (i & 31)) & 1u)) return tbx_prim_none();
-    return tbx_prim_rect(c.bg_color, T.ix[i], T.iy[i], T.iw[i], T.ih[i]);
+    if (i >= T.n_bricks || brk_alive_bit(R, i)) return tbx_prim_none();
+    /* Dead bricks that sit directly on top of each other (consecutive slots: bricks are column-major) are ONE
+     * background rectangle, emitted by the topmost of the run: the ball tunnels vertical channels, so a worn wall is
+     * a few tall holes rather than dozens of brick-sized ones.  Same pixels: the run covers exactly its bricks. */
+    if (i > 0 && brk_stacked(T, i - 1, i) && !brk_alive_bit(R, i - 1)) return tbx_prim_none();
+    int h = T.ih[i];
+    for (int j = i + 1; j < T.n_bricks && brk_stacked(T, j - 1, j) && !brk_alive_bit(R, j); j++) h += T.ih[j];
+    return tbx_prim_rect(c.bg_color, T.ix[i], T.iy[i], T.iw[i], h);
   }
   return brk_prim(R, c, tables, slot);
 }

@@ -506,7 +506,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   } else {
     /* Default: broadcast + patch (tbx_render_native.cuh) -- the base frame leaves through the TMA engine at HBM speed, what
      * differs from it is painted straight into the frame.  Envs that differ in many places (a Breakout wall with more
-     * than 24 bricks gone, an Amidar maze with more than 48 painted tiles / boxes; TBX_NATIVE_DENSE overrides) are cheaper
+     * than 20 holes, an Amidar maze with more than 48 painted tiles / boxes; TBX_NATIVE_DENSE overrides) are cheaper
      * to repaint in shared memory: the patch kernel lists them and the canvas kernel below renders exactly those.
      * TBX_NATIVE_KERNEL=canvas renders everything with the canvas kernel. */
     const char *ksel = getenv("TBX_NATIVE_KERNEL");
@@ -522,7 +522,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   if (smem_total > 220 * 1024) return set_err(TBX_EINVAL, "observation size needs more shared memory than one SM has");
   cudaStream_t s = (cudaStream_t)stream;
   if (patch_first) {
-    int thr = p->game == TBX_BREAKOUT ? 24 : p->game == TBX_AMIDAR ? 48 : INT32_MAX;
+    int thr = p->game == TBX_BREAKOUT ? 20 : p->game == TBX_AMIDAR ? 48 : INT32_MAX;
     if (const char *env = getenv("TBX_NATIVE_DENSE")) thr = atoi(env) < 0 ? INT32_MAX : atoi(env);
     RenderArgs f = a; /* same bands for the broadcast */
     if (thr != INT32_MAX) {

@@ -53,13 +53,18 @@ template <> struct Traits<TBX_BREAKOUT> {
   static __device__ __forceinline__ void group(int g, const uint32_t *R, const Table *t, int base, int &b, int &e, int &mode) { brk_group(g, R, t, base, b, e, mode); }
   static __device__ __forceinline__ void trim(int, const uint32_t *, const Cfg &, int, int &, int &) {}
   static __device__ __forceinline__ int digit_index(int s) { return s >= BRK_SLOT_SCORE && s < BRK_SLOT_BRICKS ? s - BRK_SLOT_SCORE : -1; } /* HUD digit slots */
-  /* cheap estimate of the number of entries that differ from the base frame: the dead bricks */
+  /* cheap estimate of the number of entries that differ from the base frame: the runs of dead bricks */
   template <class LD> static __device__ __forceinline__ int dense_hint(LD ld, const Cfg &c, const Table *t) { /* ld(w) = word w of the env */
     const int tbl = (int32_t)ld(TBX_W(TbxHdr, tbl));
     const Table &T = t[tbl];
     if (!(tbl == c.default_tbl && T.delta_ok)) return 1 << 20; /* not on base frame 1: every brick is an entry */
-    int n = 0;
-    for (int k = 0; k < 5; k++) n += __popc(T.all_mask[k] & ~ld(TBX_W(BrkRec, alive) + k));
+    int n = 0; /* runs of consecutive dead bricks = entries after brk_prim_delta's vertical merging (column ends ignored) */
+    uint32_t carry = 0;
+    for (int k = 0; k < 5; k++) {
+      const uint32_t dead = T.all_mask[k] & ~ld(TBX_W(BrkRec, alive) + k);
+      n += __popc(dead & ~((dead << 1) | carry));
+      carry = dead >> 31;
+    }
     return n;
   }
 };
@@ -252,7 +257,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         const bool ok = clip_prim<W>(p, r0, r1, c);
         if (!__any_sync(0xffffffffu, ok)) continue;
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
-        const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 96;
+        const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 512; /* up to a column of merged dead bricks: one thread, word stores */
         if (small) paint_small<PIX, W>(canvas, r0, c, val);
         const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
         const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
