@@ -113,3 +113,42 @@ def test_hud_digit_patches_every_value(tbx, oracle_mod, game):
     finally:
         _set_env({})
         pool.close()
+
+
+def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
+    """late-game Amidar boards (long painted corridors, painted boxes): runs of equal tiles are merged into one entry;
+    every layout and renderer against the oracle"""
+    n = 24
+    pool, ref = _advance(tbx, oracle_mod, "amidar", n, 60, 12)
+    rng = np.random.default_rng(5)
+    states = []
+    for i in range(n):
+        js = ref.state_json(i)
+        tiles = js["board"]["tiles"]
+        for _ in range(2 + i):                                   # paint random horizontal / vertical stretches of track
+            ty, tx, ln, horiz = int(rng.integers(31)), int(rng.integers(32)), int(rng.integers(1, 20)), bool(rng.integers(2))
+            for k in range(ln):
+                y, x = (ty, tx + k) if horiz else (ty + k, tx)
+                if y < 31 and x < 32 and tiles[y][x] in ("Unpainted", "ChaseMarker"):
+                    tiles[y][x] = "Painted"
+        for b in js["board"]["boxes"][: i % 7]:
+            b["painted"] = True
+        ref.write_state_json(i, js)
+        states.append(js)
+    pool.write_state_json(states)
+    keys = ("TBX_NATIVE_KERNEL", "TBX_NATIVE_DENSE", "TBX_AREA_LCAP", "TBX_AREA_KERNEL")
+    try:
+        for mode, omode in (("gray84", "gray84"), ("rgb", "rgb"), ("gray", "gray"), ("rgba", "rgba")):
+            want = ref.render(omode).reshape(n, -1)
+            for v in ({}, {"TBX_NATIVE_KERNEL": "canvas"}, {"TBX_NATIVE_DENSE": "-1"}, {"TBX_NATIVE_DENSE": "4"}, {"TBX_AREA_LCAP": "16"},
+                      {"TBX_AREA_KERNEL": "cta"}):
+                for k in keys:
+                    os.environ.pop(k, None)
+                os.environ.update(v)
+                got = pool.render(obs=mode).cpu().numpy().reshape(n, -1)
+                bad = np.argwhere(got != want)
+                assert bad.size == 0, (mode, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+        pool.close()

@@ -479,13 +479,23 @@ TBX_HD TbxPrim ami_prim(const uint32_t *R, const AmiCfg &c, const AmiTable *tabl
  * differs from the config board, painted in their current look. */
 TBX_HD int ami_tile_look(int t) { return t == TBX_TILE_EMPTY ? 0 : t == TBX_TILE_PAINTED ? 2 : 1; }
 TBX_HD int ami_base_id(const uint32_t *, const AmiCfg &, const AmiTable *) { return 1; }
+/* the look of tile (tx, ty) if it differs from the config board's, else -1 */
+TBX_HD int ami_delta_look(const uint32_t *R, const AmiCfg &c, int tx, int ty) {
+  const int look = ami_tile_look((int)((R[AMI_W(tiles) + 2 * ty + (tx >> 4)] >> (2 * (tx & 15))) & 3u));
+  const int ref = ami_tile_look((int)((c.board[ty][tx >> 4] >> (2 * (tx & 15))) & 3u));
+  return look == ref ? -1 : look;
+}
 TBX_HD TbxPrim ami_prim_delta(const uint32_t *R, const AmiCfg &c, const AmiTable *tables, int slot, int base) {
   if (base == 1 && slot < AMI_SLOT_BOXES) {
-    int tx = slot & 31, ty = slot >> 5;
-    int look = ami_tile_look((int)((R[AMI_W(tiles) + 2 * ty + (tx >> 4)] >> (2 * (tx & 15))) & 3u));
-    int ref = ami_tile_look((int)((c.board[ty][tx >> 4] >> (2 * (tx & 15))) & 3u));
-    if (look == ref) return tbx_prim_none();
-    return tbx_prim_rect(look == 0 ? c.bg_color : look == 2 ? c.painted_color : c.unpainted_color, AMI_OFF_X + 4 * tx, AMI_OFF_Y + 5 * ty, 4, 5);
+    const int tx = slot & 31, ty = slot >> 5;
+    const int look = ami_delta_look(R, c, tx, ty);
+    if (look < 0) return tbx_prim_none();
+    /* Horizontally adjacent tiles that differ from the config board in the same way are ONE rectangle, emitted by the
+     * leftmost of the run (slots are row-major): painted corridors are long lines, not hundreds of 4 x 5 cells. */
+    if (tx > 0 && ami_delta_look(R, c, tx - 1, ty) == look) return tbx_prim_none();
+    int len = 1;
+    while (tx + len < TBX_AMI_BW && ami_delta_look(R, c, tx + len, ty) == look) len++;
+    return tbx_prim_rect(look == 0 ? c.bg_color : look == 2 ? c.painted_color : c.unpainted_color, AMI_OFF_X + 4 * tx, AMI_OFF_Y + 5 * ty, 4 * len, 5);
   }
   return ami_prim(R, c, tables, slot);
 }
