@@ -8,6 +8,10 @@ device, advance every env one frame (tbx_step), render every env (tbx_render).  
     python bench.py [--gpus N] [--steps K] [--warmup W] [--game G] [--envs E] [--obs gray84|gray|rgb|rgba]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
     python bench.py --impl reference ...    times the CPU restatement of the reference path (oracle/) on the host cores
+    python bench.py --wrapped [--game G]    supplementary: the fused DeepMind wrapper stack (agent steps/s; 1 agent step = 4 frames)
+    python bench.py --mixed 1048576 [--gpus N under torchrun]    supplementary: BASELINE configs[4], 1/3 of the envs per game,
+                                            NCCL all-reduce of the episode statistics every 256 steps
+    python bench.py --policy track --presteps 3000    supplementary: mid-game Breakout states (scripted ball-tracking policy)
 """
 import argparse
 import json
