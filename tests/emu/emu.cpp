@@ -11,6 +11,7 @@
 #include "../../toybox_b200/csrc/tbx_breakout.h"
 #include "../../toybox_b200/csrc/tbx_space_invaders.h"
 #include "../../toybox_b200/csrc/tbx_amidar.h"
+#include "../../toybox_b200/csrc/tbx_direct.h"
 #include <string.h>
 #include <stdlib.h>
 #include <string>
@@ -188,6 +189,89 @@ int emu_render_fast(Emu *e, int out_w, int out_h, uint8_t *out) {
         const int iv = tbx_f2i_rn(v);
         out[dy * out_w + dx] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
       }
+  }
+  return 0;
+}
+
+/* The DIRECT INTER_AREA algorithm (tbx_direct.h, tbx_render_direct.cuh) on the host, phase by phase as the kernel runs
+ * it: base down-sample, wall rows from the look-up tables (only the output words / rows a dead brick feeds), HUD digit
+ * patches, then the movers' footprints evaluated tap by tap.  Returns 1 when the env is one the kernel hands to the
+ * general tile kernel (not rendered here), 0 when `out` holds the frame; must then equal emu_render(mode 3). */
+int emu_render_direct(Emu *e, int out_w, int out_h, uint8_t *out) {
+  const int W = e->info->width, H = e->info->height;
+  tbx::ResizeTab rs;
+  TbxAreaPlan pl;
+  try { tbx::build_resize(W, H, out_w, out_h, rs); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  if (!tbx::build_area_plan(rs, pl)) { g_err = "size pair outside the fused kernel's limits"; return -1; }
+  if (e->game != TBX_BREAKOUT) return 1;
+  const BrkTable &dt = e->brk_tables[e->cfg.brk.default_tbl];
+  std::vector<uint32_t> rgba((size_t)W * H);
+  std::vector<uint8_t> base0((size_t)W * H), base1((size_t)W * H);
+  tbx::build_base_frame(e->cfg, &dt, 0, rgba.data());
+  tbx::frame_to_gray(rgba.data(), W * H, base0.data());
+  tbx::build_base_frame(e->cfg, &dt, 1, rgba.data());
+  tbx::frame_to_gray(rgba.data(), W * H, base1.data());
+  static TbxBrkDirect A;
+  tbx::build_brk_direct(e->cfg, dt, rs, pl, base0.data(), A);
+  const uint32_t *R = e->rec.data();
+  if (!A.ok || (int32_t)R[TBX_HW(tbl)] != e->cfg.brk.default_tbl) return 1;
+  std::vector<TbxDigitPatch> patches((size_t)TBX_DP_SLOTS * 10);
+  tbx::build_digit_patches(e->cfg, &dt, rs, pl, base1.data(), patches.data());
+  TbxMover mv[BRK_N_MOVERS];
+  int fx0[BRK_N_MOVERS], fx1[BRK_N_MOVERS], fy0[BRK_N_MOVERS], fy1[BRK_N_MOVERS];
+  for (int m = 0; m < BRK_N_MOVERS; m++) {
+    mv[m] = brk_mover(R, e->cfg.brk, A, m);
+    if (mv[m].x0 >= mv[m].x1) continue;
+    fx0[m] = pl.xdlo[mv[m].x0]; fx1[m] = pl.xdhi[mv[m].x1 - 1]; fy0[m] = pl.ydlo[mv[m].y0]; fy1[m] = pl.ydhi[mv[m].y1 - 1];
+    if (fy0[m] <= A.hud_dyhi) return 1;
+  }
+  const int32_t fields[2] = {(int32_t)R[TBX_HW(score)], (int32_t)R[TBX_HW(lives)]};
+  for (int f = 0; f < 2; f++)
+    for (int k = 0; k < TBX_MAX_DIGITS; k++) {
+      const int d = tbx_digit_at(fields[f], k);
+      if (d >= 0 && patches[(f * 10 + k) * 10 + d].w == 0) return 1;
+    }
+  tbx::area_resize(base1.data(), rs, out);
+  /* wall */
+  const uint32_t *alive = R + BRK_W(alive);
+  const uint32_t full = (1u << A.nrows) - 1u;
+  uint32_t deadcols = 0, deadrows = 0, rowmask[TBX_BRK_MAX_ROWS] = {0};
+  for (int c = 0; c < A.ncols; c++) {
+    const uint32_t v = brk_col_bits(alive, A.nrows, c);
+    if (v != full) deadcols |= 1u << c;
+    deadrows |= ~v & full;
+    for (int r = 0; r < A.nrows; r++) rowmask[r] |= ((v >> r) & 1u) << c;
+  }
+  if (deadcols) {
+    std::vector<float> hd((size_t)A.nrows * out_w);
+    for (int r = 0; r < A.nrows; r++) for (int dx = 0; dx < out_w; dx++) hd[(size_t)r * out_w + dx] = brk_direct_h(A, r, rowmask[r], dx);
+    int rlo = -1, rhi = -1;
+    for (int dy = A.wdy0; dy <= A.wdy1; dy++) if (A.dyrows[dy] & deadrows) { if (rlo < 0) rlo = dy; rhi = dy; }
+    for (int dy = rlo; rlo >= 0 && dy <= rhi; dy++)
+      for (int w = 0; w < out_w / 4; w++) {
+        if (!(A.wordcols[w] & deadcols)) continue;
+        for (int dx = 4 * w; dx < 4 * w + 4; dx++) out[dy * out_w + dx] = brk_direct_wall_pixel<TBX_AREA_MAX_TAPS>(A, pl, hd.data(), out_w, dx, dy);
+      }
+  }
+  /* HUD digits */
+  for (int f = 0; f < 2; f++)
+    for (int k = 0; k < TBX_MAX_DIGITS; k++) {
+      const int d = tbx_digit_at(fields[f], k);
+      if (d < 0) continue;
+      const TbxDigitPatch &P = patches[(f * 10 + k) * 10 + d];
+      for (int r = 0; r < P.h; r++) for (int cc = 0; cc < P.w; cc++) out[(P.y0 + r) * out_w + P.x0 + cc] = P.px[r * P.w + cc];
+    }
+  /* movers */
+  for (int m = 0; m < BRK_N_MOVERS; m++) {
+    if (mv[m].x0 >= mv[m].x1) continue;
+    const int sx0 = pl.xs0[fx0[m]], sx1 = pl.xs0[fx1[m]] + TBX_AREA_MAX_TAPS, sy0 = pl.ys0[fy0[m]], sy1 = pl.ys0[fy1[m]] + TBX_AREA_MAX_TAPS;
+    uint32_t near = 0;
+    for (int q = 0; q < BRK_N_MOVERS; q++)
+      if (mv[q].x0 < mv[q].x1 && mv[q].x0 < sx1 && mv[q].x1 > sx0 && mv[q].y0 < sy1 && mv[q].y1 > sy0) near |= 1u << q;
+    const bool wall = sy0 < A.wy0 + A.nrows * A.bh && sy1 > A.wy0;
+    for (int dy = fy0[m]; dy <= fy1[m]; dy++)
+      for (int dx = fx0[m]; dx <= fx1[m]; dx++)
+        out[dy * out_w + dx] = brk_direct_pixel<TBX_AREA_MAX_TAPS, TBX_AREA_MAX_TAPS>(A, pl, base0.data(), alive, mv, near, wall, dx, dy);
   }
   return 0;
 }

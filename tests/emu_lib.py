@@ -107,6 +107,16 @@ class Emu:
             raise ValueError(self.L.emu_last_error().decode())
         return out
 
+    def render_direct(self, out_w=84, out_h=84):
+        """The direct INTER_AREA algorithm (tbx_direct.h) emulated on the host; None when the env is one the kernel hands
+        to the general tile kernel."""
+        out = np.empty((out_h, out_w), np.uint8)
+        self.L.emu_render_direct.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        rc = self.L.emu_render_direct(self.h, out_w, out_h, out.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            raise ValueError(self.L.emu_last_error().decode())
+        return None if rc else out
+
     def state_json(self):
         return json.loads(_take(self.L.emu_state_to_json(self.h)))
 

@@ -8,8 +8,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 GAMES = ["breakout", "amidar", "space_invaders"]
-VARIANTS = [{}, {"TBX_AREA_DIGIT_CACHE": "0"}, {"TBX_AREA_LCAP": "24"}, {"TBX_AREA_LCAP": "3"}, {"TBX_AREA_KERNEL": "cta"}, {"TBX_AREA_THREADS": "128"},
-            {"TBX_AREA_TILE_H": "4", "TBX_AREA_MAX_RUN": "8"}, {"TBX_AREA_TILE_H": "16"}, {"TBX_AREA_MAX_RUN": "1", "TBX_AREA_LCAP": "40"}]
+TILE = {"TBX_AREA_KERNEL": "tile"}        # Breakout: without the direct kernel (tbx_render_direct.cuh) in front of the tile kernel
+VARIANTS = [{}, TILE, dict(TILE, TBX_AREA_DIGIT_CACHE="0"), dict(TILE, TBX_AREA_LCAP="24"), dict(TILE, TBX_AREA_LCAP="3"), {"TBX_AREA_KERNEL": "cta"},
+            dict(TILE, TBX_AREA_THREADS="128"), dict(TILE, TBX_AREA_TILE_H="4", TBX_AREA_MAX_RUN="8"), dict(TILE, TBX_AREA_TILE_H="16"),
+            dict(TILE, TBX_AREA_MAX_RUN="1", TBX_AREA_LCAP="40"), {"TBX_AREA_LCAP": "3"}]
 SIZES = [(84, 84), (96, 80), (64, 64), (48, 60), (100, 37)]
 
 
@@ -105,11 +107,59 @@ def test_hud_digit_patches_every_value(tbx, oracle_mod, game):
             ref.write_state_json(i, js)
         for ow, oh in ((84, 84), (96, 80), (64, 64)):
             want = ref.render("gray84", ow, oh).reshape(n, -1)
-            for v in ({}, {"TBX_AREA_DIGIT_CACHE": "0"}):
+            for v in ({}, TILE, dict(TILE, TBX_AREA_DIGIT_CACHE="0")):
                 _set_env(v)
                 got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
                 bad = np.argwhere(got != want)
                 assert bad.size == 0, (game, ow, oh, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+    finally:
+        _set_env({})
+        pool.close()
+
+
+def test_direct_kernel_mixed_pool(tbx, oracle_mod):
+    """Breakout's direct INTER_AREA kernel on a pool that mixes the states it covers (worn walls, several balls, wide and
+    misplaced paddles, multi-digit scores) with states it hands to the tile kernel (custom brick tables, a ball inside the
+    HUD rows, scores whose digits are clipped by the frame) -- every env must come out bit-exact, twice in a row (the
+    hand-over list empties itself), and again after further steps."""
+    n = 203
+    pool, ref = _advance(tbx, oracle_mod, "breakout", n, 300, 5)
+    rng = np.random.default_rng(11)
+    states = []
+    for i in range(n):
+        js = ref.state_json(i)
+        for k in rng.choice(108, size=int(rng.integers(0, 108)) if i % 3 else 0, replace=False):
+            js["bricks"][int(k)]["alive"] = False
+        if i % 5 == 1:
+            js["balls"] = [{"position": {"x": float(rng.uniform(0, 240)), "y": float(rng.uniform(20, 170))}, "velocity": {"x": 1.0, "y": -1.0}}
+                           for _ in range(int(rng.integers(0, 5)))]
+        if i % 7 == 2:
+            js["paddle"]["position"] = {"x": float(rng.uniform(0, 240)), "y": float(rng.choice([143.0, 60.0, 50.5, 158.0]))}
+            js["paddle_width"] = float(rng.choice([24.0, 48.0, 7.0, 300.0]))
+            js["ball_radius"] = float(rng.choice([2.0, 5.5, 0.5]))
+        js["score"] = int(rng.choice([0, 7, 42, 860, 123456, 123456789]))
+        js["lives"] = int(rng.choice([5, 1, 13]))
+        if i % 11 == 3:
+            js["bricks"][int(rng.integers(108))]["position"]["x"] += 3.0          # a custom brick table: the tile kernel's env
+        if i % 13 == 4:
+            js["balls"] = [{"position": {"x": 100.0, "y": 5.0}, "velocity": {"x": 1.0, "y": 1.0}}]   # inside the HUD rows
+        ref.write_state_json(i, js)
+        states.append(js)
+    pool.write_state_json(states)
+    legal = np.asarray(oracle_mod.LEGAL["breakout"], np.int32)
+    try:
+        for rnd in range(3):
+            for ow, oh in ((84, 84), (96, 80), (64, 64)):
+                want = ref.render("gray84", ow, oh).reshape(n, -1)
+                for v in ({}, {}, TILE):
+                    _set_env(v)
+                    got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
+                    bad = np.argwhere(got != want)
+                    assert bad.size == 0, (rnd, ow, oh, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+            for t in range(40):
+                acts = legal[[oracle_mod.action_index(0xB200, i, 1000 * rnd + t, len(legal)) for i in range(n)]]
+                pool.apply_ale_action(acts, auto_reset=True)
+                ref.step(acts, auto_reset=True)
     finally:
         _set_env({})
         pool.close()

@@ -12,7 +12,7 @@ _LIB = None
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
-SOURCES = ["tbx_pool.cu", "tbx_host.cpp"]
+SOURCES = ["tbx_pool.cu", "tbx_direct.cu", "tbx_host.cpp"]
 
 
 def _stale():
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TBX_NVCC_EXTRA", "").split()          # tuning experiments, e.g. -DTBX_RENDER_THREADS=128
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + [os.path.join(_CSRC, s) for s in SOURCES]
+    cmd = [nvcc, "-t", "0"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + [os.path.join(_CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return _SO
 

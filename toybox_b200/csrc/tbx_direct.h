@@ -1,0 +1,145 @@
+/* tbx_direct.h -- DIRECT evaluation of the INTER_AREA (WarpFrame, 84x84 gray) observation: closed forms per game
+ * instead of "paint a canvas, then resolve it".
+ *
+ * The reference produces the observation as get_state() (toybox/envs/atari/base.py:109) followed by
+ * cv2.resize(..., INTER_AREA) (baselines/baselines/common/atari_wrappers.py:243).  An output pixel is
+ *     round( sum_k yalpha[k][dy] * ( sum_t xalpha[t][dx] * src[ys0[dy] + k][xs0[dx] + t] ) )      (f32, this order)
+ * and the native frame `src` is never needed as a whole:
+ *   - where the frame is a regular GRID of cells whose rows repeat (Breakout's brick wall), the inner sum of one
+ *     source row depends on the alive bits of at most two neighbouring cells: it is a table look-up (host-built with
+ *     the very same f32 operations), and one look-up serves every source row of the cell row;
+ *   - where a few small MOVERS (paddle, balls) sit on top, only the output pixels their rectangles feed are evaluated,
+ *     tap by tap, with an analytic painter's algorithm: base pixel, then grid cell, then the movers in draw order;
+ *   - HUD digits are pre-resolved patches (TbxDigitPatch), everything else is the pre-computed down-sample of the base
+ *     frame.
+ * The functions here are TBX_HD: the kernels of tbx_render_direct.cuh and the CPU-tier emulation (tests/emu) run the
+ * same code.  Envs the closed forms do not cover (custom brick tables, movers inside the HUD rows) are rendered by the
+ * general tile kernel (tbx_render_area.cuh).
+ */
+#ifndef TBX_DIRECT_H
+#define TBX_DIRECT_H
+#include "tbx_breakout.h"
+#include "tbx_space_invaders.h"
+#include "tbx_amidar.h"
+
+/* a clipped rectangle of the draw list with its gray value; x0 >= x1: empty */
+struct TbxMover { int x0, y0, x1, y1; uint32_t gray; };
+
+/* ------------------------------------------------------------------ Breakout */
+#define TBX_BD_MAX_STATIC 16
+#define BRK_N_MOVERS (1 + TBX_BRK_MAX_BALLS) /* paddle, balls in draw order */
+typedef struct {
+  int32_t ok;                    /* 0: this (config, output size) pair is rendered by the tile kernel */
+  int32_t ncols, nrows;          /* the default table is a grid of ncols x nrows bricks, index = col * nrows + row */
+  int32_t wx0, wy0, bw, bh;      /* origin of the grid and brick size in pixels */
+  int32_t wdy0, wdy1;            /* output rows fed by the wall's source rows (inclusive) */
+  int32_t hud_dyhi;              /* last output row fed by a HUD digit row */
+  int32_t n_static, _pad;
+  uint32_t paddle_gray, ball_gray;
+  uint8_t xcol[TBX_AREA_MAX_SRC]; /* brick column of source column x, 255 = none */
+  uint8_t yrow[TBX_AREA_MAX_SRC]; /* brick row of source row y, 255 = none */
+  uint8_t col0[TBX_AREA_MAX_DST]; /* per output column: the taps touch brick columns col0 and col0 + 1 only */
+  uint8_t dyrows[TBX_AREA_MAX_DST]; /* per output row: mask of the brick rows its taps touch */
+  uint8_t hsel[TBX_AREA_MAX_DST][TBX_AREA_MAX_TAPS]; /* per output row and tap: H row -- < nrows: brick row, else static row (- nrows) */
+  uint32_t wordcols[32];          /* per output word (4 columns): mask of the brick columns that feed it */
+  uint8_t brickgray[TBX_BRK_MAX_BRICKS];
+  float hlut[TBX_BRK_MAX_ROWS][4][TBX_AREA_MAX_DST];  /* [brick row][alive(col0) | alive(col0 + 1) << 1][dx] */
+  float hstatic[TBX_BD_MAX_STATIC][TBX_AREA_MAX_DST]; /* horizontal sums of the base-frame-0 rows around the wall */
+} TbxBrkDirect;
+
+/* paddle (m == 0) or ball m - 1 as a clipped rectangle */
+TBX_HD TbxMover brk_mover(const uint32_t *R, const BrkCfg &c, const TbxBrkDirect &A, int m) {
+  TbxMover v; v.x0 = v.y0 = v.x1 = v.y1 = 0; v.gray = m == 0 ? A.paddle_gray : A.ball_gray;
+  if (m < 0 || m >= BRK_N_MOVERS) return v;
+  const TbxPrim p = brk_prim(R, c, (const BrkTable *)0, m == 0 ? BRK_SLOT_PADDLE : BRK_SLOT_BALLS + m - 1); /* these slots never read the tables */
+  if (p.h <= 0) return v;
+  const int x0 = p.x < 0 ? 0 : p.x, y0 = p.y < 0 ? 0 : p.y;
+  const int x1 = p.x + p.w > TBX_BRK_W ? TBX_BRK_W : p.x + p.w, y1 = p.y + p.h > TBX_BRK_H ? TBX_BRK_H : p.y + p.h;
+  if (x0 >= x1 || y0 >= y1) return v;
+  v.x0 = x0; v.y0 = y0; v.x1 = x1; v.y1 = y1;
+  return v;
+}
+
+/* alive bits of brick column c (bit r = row r) */
+TBX_HD uint32_t brk_col_bits(const uint32_t *alive, int nrows, int c) {
+  const int i0 = c * nrows, w = i0 >> 5, s = i0 & 31;
+  const uint32_t lo = alive[w], hi = w < 4 ? alive[w + 1] : 0u;
+  const uint32_t v = s ? (lo >> s) | (hi << (32 - s)) : lo;
+  return v & ((1u << nrows) - 1u);
+}
+
+/* gray value of native-frame pixel (x, y): base frame 0, then the brick grid, then the movers in `near` in draw order */
+TBX_HD uint32_t brk_direct_src(const TbxBrkDirect &A, const uint8_t *base0, const uint32_t *alive, const TbxMover *mv, uint32_t near, bool wall,
+                               int x, int y) {
+  uint32_t v = base0[y * TBX_BRK_W + x];
+  if (wall) {
+    const uint32_t c = A.xcol[x], r = A.yrow[y];
+    if ((c | r) != 255u) { /* both are < 255: a brick cell */
+      const uint32_t i = c * (uint32_t)A.nrows + r;
+      if ((alive[i >> 5] >> (i & 31)) & 1u) v = A.brickgray[i];
+    }
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < BRK_N_MOVERS; m++)
+    if ((near >> m) & 1u)
+      if ((unsigned)(x - mv[m].x0) < (unsigned)(mv[m].x1 - mv[m].x0) && (unsigned)(y - mv[m].y0) < (unsigned)(mv[m].y1 - mv[m].y0)) v = mv[m].gray;
+  return v;
+}
+
+/* one output pixel, every tap evaluated analytically (zero-padded TX x TY taps in cv2's order) */
+template <int TX, int TY>
+TBX_HD uint8_t brk_direct_pixel(const TbxBrkDirect &A, const TbxAreaPlan &pl, const uint8_t *base0, const uint32_t *alive, const TbxMover *mv, uint32_t near,
+                                bool wall, int dx, int dy) {
+  const int xs = pl.xs0[dx], ys = pl.ys0[dy];
+  float acc = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < TY; k++) {
+    const int y = ys + k < TBX_BRK_H ? ys + k : TBX_BRK_H - 1; /* surplus taps carry zero weights: any in-frame pixel will do */
+    float h = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int t = 0; t < TX; t++) {
+      const int x = xs + t < TBX_BRK_W ? xs + t : TBX_BRK_W - 1;
+      const float p = tbx_fmul(tbx_u8f(brk_direct_src(A, base0, alive, mv, near, wall, x, y)), pl.xalpha[t][dx]);
+      h = t == 0 ? p : tbx_fadd(h, p);
+    }
+    const float bh = tbx_fmul(pl.yalpha[k][dy], h);
+    acc = k == 0 ? bh : tbx_fadd(acc, bh);
+  }
+  const int iv = tbx_f2i_rn_small(acc);
+  return (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+}
+
+/* the wall: horizontal sum of brick row r at output column dx from the row's alive mask (bit c = column c alive) */
+TBX_HD float brk_direct_h(const TbxBrkDirect &A, int r, uint32_t rowmask, int dx) { return A.hlut[r][(rowmask >> A.col0[dx]) & 3u][dx]; }
+/* ... and the output pixel from the H rows: hdyn[r * hstride + dx] holds brk_direct_h of brick row r */
+template <int TY>
+TBX_HD uint8_t brk_direct_wall_pixel(const TbxBrkDirect &A, const TbxAreaPlan &pl, const float *hdyn, int hstride, int dx, int dy) {
+  float acc = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < TY; k++) {
+    const int sel = A.hsel[dy][k];
+    const float h = sel < A.nrows ? hdyn[sel * hstride + dx] : A.hstatic[sel - A.nrows][dx];
+    const float bh = tbx_fmul(pl.yalpha[k][dy], h);
+    acc = k == 0 ? bh : tbx_fadd(acc, bh);
+  }
+  const int iv = tbx_f2i_rn_small(acc);
+  return (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+}
+
+/* HUD digit k (0 = least significant) of a field value: -1 = not shown (tbx_prim_digit) */
+TBX_HD int tbx_digit_at(int value, int k) {
+  uint32_t q = value < 0 ? 0u : (uint32_t)value;
+  for (int i = 0; i < k; i++) q /= 10u;
+  if (k > 0 && q == 0) return -1;
+  return (int)(q % 10u);
+}
+
+#endif

@@ -931,4 +931,103 @@ void build_digit_patches(const Config &c, const BrkTable *brk_default, const Res
   }
 }
 
+/* ------------------------------------------------------------------ direct INTER_AREA tables (tbx_direct.h) */
+/* horizontal sum of one source row at output column dx: the kernels' zero-padded tap order */
+static float hsum_row(const uint8_t *row, int W, const TbxAreaPlan &pl, int dx) {
+  float h = 0.0f;
+  for (int t = 0; t < TBX_AREA_MAX_TAPS; t++) {
+    const int x = pl.xs0[dx] + t < W ? pl.xs0[dx] + t : W - 1;
+    const float p = tbx_fmul((float)row[x], pl.xalpha[t][dx]);
+    h = t == 0 ? p : tbx_fadd(h, p);
+  }
+  return h;
+}
+void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, const TbxAreaPlan &pl, const uint8_t *base0, TbxBrkDirect &A) {
+  memset(&A, 0, sizeof A);
+  const int W = TBX_BRK_W, H = TBX_BRK_H, dw = pl.dw, dh = pl.dh;
+  if (c.game != TBX_BREAKOUT || !t.delta_ok || dw % 4 != 0 || dw > TBX_AREA_MAX_DST || dh > TBX_AREA_MAX_DST || pl.tx > 5 || pl.ty > 4) return;
+  const int n = t.n_bricks, nrows = c.brk.n_rows;
+  if (n <= 0 || nrows <= 0 || nrows > TBX_BRK_MAX_ROWS || n % nrows != 0) return;
+  const int ncols = n / nrows;
+  if (ncols > 31) return;
+  const int bw = t.iw[0], bh = t.ih[0], wx0 = t.ix[0], wy0 = t.iy[0];
+  if (bw <= 0 || bh <= 0 || wx0 < 0 || wy0 < 0 || wx0 + ncols * bw > W || wy0 + nrows * bh > H) return;
+  for (int i = 0; i < n; i++) {
+    const int col = i / nrows, row = i % nrows;
+    if (t.ix[i] != wx0 + col * bw || t.iy[i] != wy0 + row * bh || t.iw[i] != bw || t.ih[i] != bh) return;
+    A.brickgray[i] = (uint8_t)tbx_luma(t.color[i]);
+  }
+  A.ncols = ncols; A.nrows = nrows; A.wx0 = wx0; A.wy0 = wy0; A.bw = bw; A.bh = bh;
+  A.paddle_gray = tbx_luma(c.brk.paddle_color); A.ball_gray = tbx_luma(c.brk.ball_color);
+  memset(A.xcol, 255, sizeof A.xcol);
+  memset(A.yrow, 255, sizeof A.yrow);
+  for (int x = wx0; x < wx0 + ncols * bw; x++) A.xcol[x] = (uint8_t)((x - wx0) / bw);
+  for (int y = wy0; y < wy0 + nrows * bh; y++) A.yrow[y] = (uint8_t)((y - wy0) / bh);
+  /* base frame 0 must look the same on every source row of a brick row (it holds the side walls and background only) */
+  for (int r = 0; r < nrows; r++)
+    for (int y = wy0 + r * bh + 1; y < wy0 + (r + 1) * bh; y++)
+      if (memcmp(base0 + (size_t)y * W, base0 + (size_t)(wy0 + r * bh) * W, W) != 0) return;
+  /* per output column: the brick columns its real taps touch -- at most two neighbours -- and the look-up table */
+  std::vector<uint8_t> row(W);
+  for (int dx = 0; dx < dw; dx++) {
+    int cmin = 255, cmax = -1;
+    uint32_t cols = 0;
+    for (int k = rs.x.start[dx]; k < rs.x.start[dx + 1]; k++) {
+      const int cc = A.xcol[rs.x.si[k]];
+      if (cc == 255) continue;
+      cols |= 1u << cc;
+      if (cc < cmin) cmin = cc;
+      if (cc > cmax) cmax = cc;
+    }
+    if (cmax >= 0 && cmax - cmin > 1) return;
+    int c0 = cmax < 0 ? 0 : cmin;
+    if (c0 > ncols - 2) c0 = ncols - 2 < 0 ? 0 : ncols - 2;
+    A.col0[dx] = (uint8_t)c0;
+    A.wordcols[dx >> 2] |= cols;
+    for (int r = 0; r < nrows; r++)
+      for (int bits = 0; bits < 4; bits++) {
+        memcpy(row.data(), base0 + (size_t)(wy0 + r * bh) * W, W);
+        for (int j = 0; j < 2; j++) {
+          const int cc = c0 + j;
+          if (cc >= ncols || !((bits >> j) & 1)) continue;
+          for (int x = wx0 + cc * bw; x < wx0 + (cc + 1) * bw; x++) row[x] = A.brickgray[cc * nrows + r];
+        }
+        A.hlut[r][bits][dx] = hsum_row(row.data(), W, pl, dx);
+      }
+  }
+  /* per output row of the wall: which H row every tap reads */
+  const int wy1 = wy0 + nrows * bh;
+  A.wdy0 = pl.ydlo[wy0]; A.wdy1 = pl.ydhi[wy1 - 1];
+  if (A.wdy1 - A.wdy0 + 1 > 32) return;
+  for (int dy = A.wdy0; dy <= A.wdy1; dy++) {
+    const int nreal = rs.y.start[dy + 1] - rs.y.start[dy];
+    for (int k = 0; k < TBX_AREA_MAX_TAPS; k++) {
+      if (k >= nreal) { A.hsel[dy][k] = A.hsel[dy][0]; continue; } /* zero weight: any finite row */
+      const int y = pl.ys0[dy] + k;
+      if (A.yrow[y] != 255) { A.hsel[dy][k] = A.yrow[y]; A.dyrows[dy] |= (uint8_t)(1u << A.yrow[y]); continue; }
+      float hrow[TBX_AREA_MAX_DST];
+      for (int dx = 0; dx < dw; dx++) hrow[dx] = hsum_row(base0 + (size_t)y * W, W, pl, dx);
+      int s = 0;
+      for (; s < A.n_static; s++) if (memcmp(A.hstatic[s], hrow, sizeof(float) * dw) == 0) break;
+      if (s == A.n_static) {
+        if (A.n_static == TBX_BD_MAX_STATIC) return;
+        memcpy(A.hstatic[A.n_static++], hrow, sizeof(float) * dw);
+      }
+      A.hsel[dy][k] = (uint8_t)(nrows + s);
+    }
+  }
+  /* HUD digit rows (score, lives) must stay clear of the wall's output rows */
+  {
+    std::vector<uint32_t> rec(TBX_WORDS(BrkRec), 0);
+    TbxHdr &h = *reinterpret_cast<TbxHdr *>(rec.data());
+    h.score = 1999999999; h.lives = 1999999999;
+    int y1 = 0;
+    for (int s = BRK_SLOT_SCORE; s < BRK_SLOT_BRICKS; s++) { const TbxPrim p = brk_prim(rec.data(), c.brk, &t, s); if (p.h > 0 && p.y + p.h > y1) y1 = p.y + p.h; }
+    if (y1 > H) y1 = H;
+    A.hud_dyhi = y1 > 0 ? pl.ydhi[y1 - 1] : -1;
+    if (A.wdy0 <= A.hud_dyhi) return;
+  }
+  A.ok = 1;
+}
+
 } /* namespace tbx */

@@ -5,6 +5,7 @@
 #ifndef TBX_HOST_H
 #define TBX_HOST_H
 #include "tbx_records.h"
+#include "tbx_direct.h"
 #include "tbx_json.h"
 #include <string>
 #include <vector>
@@ -81,6 +82,9 @@ void area_resize(const uint8_t *gray, const ResizeTab &t, uint8_t *out);
 /* the TBX_DP_SLOTS x 10 digit patches of base frame `base_id` (gray) for one output size; out[slot * 10 + digit] */
 void build_digit_patches(const Config &c, const BrkTable *brk_default, const ResizeTab &t, const TbxAreaPlan &plan, const uint8_t *base_gray,
                          TbxDigitPatch *out);
+/* closed-form tables of the direct INTER_AREA kernel (tbx_direct.h) for the config's default brick table and one output
+ * size; out.ok == 0 when the pair is outside its limits (irregular brick grid, output width not a multiple of 4 ...) */
+void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray, TbxBrkDirect &out);
 int digit_slot0(int game);   /* first draw-list slot of the HUD digit fields */
 int digit_slots(int game);   /* how many consecutive digit slots follow */
 

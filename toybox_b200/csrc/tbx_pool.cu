@@ -3,6 +3,7 @@
 #include "tbx_kernels.cuh"
 #include "tbx_wrap.cuh"
 #include "tbx_fields.h"
+#include "tbx_direct_launch.h"
 #include <map>
 #include <new>
 #include <string>
@@ -20,7 +21,10 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
     if (e_ != cudaSuccess) return set_err(TBX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct AreaRes { TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; TbxDigitPatch *d_patches[2]; int dw, dh, tx, ty; };
+struct AreaRes {
+  TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; TbxDigitPatch *d_patches[2]; int dw, dh, tx, ty;
+  void *d_direct; int direct_ok; /* closed-form tables of the direct kernel (tbx_direct.h), NULL / 0 when the pair is not covered */
+};
 static void drop_render_cache(struct tbx_pool *p);
 
 struct tbx_pool {
@@ -42,6 +46,7 @@ struct tbx_pool {
   std::vector<uint8_t> h_base_gray[2];
   std::map<std::pair<int, int>, struct AreaRes> area;
   int32_t *d_dense; /* [0] = count, [8..] = env ids the patch kernel left to the canvas kernel */
+  int32_t *d_fb;    /* [0] = count, [1] = finished CTAs, [8..] = env ids the direct INTER_AREA kernel left to the tile kernel */
   /* tbx_step_host staging */
   cudaStream_t hs;
   int32_t *h_actions_dev, *h_reward_dev, *h_score_dev, *h_lives_dev;
@@ -107,7 +112,7 @@ int tbx_pool_destroy(tbx_pool *p) {
   if (!p) return TBX_OK;
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
-  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal); cudaFree(p->d_dense);
+  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal); cudaFree(p->d_dense); cudaFree(p->d_fb);
   drop_render_cache(p);
   cudaFree(p->h_actions_dev); cudaFree(p->h_reward_dev); cudaFree(p->h_score_dev); cudaFree(p->h_lives_dev); cudaFree(p->h_done_dev); cudaFree(p->h_obs_dev);
   if (p->hs) cudaStreamDestroy(p->hs);
@@ -129,7 +134,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
   p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = p->d_base_rgb[0] = p->d_base_rgb[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
-  p->hs = 0; p->d_dense = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
+  p->hs = 0; p->d_dense = 0; p->d_fb = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
     tbx::default_config(g, p->cfg);
@@ -251,7 +256,7 @@ int tbx_check(tbx_pool *p, void *stream) {
 /* ---- render */
 static void drop_render_cache(tbx_pool *p) {
   for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); cudaFree(p->d_base_rgb[b]); p->d_base_gray[b] = p->d_base_rgba[b] = p->d_base_rgb[b] = 0; }
-  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); cudaFree(kv.second.d_patches[0]); cudaFree(kv.second.d_patches[1]); }
+  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); cudaFree(kv.second.d_patches[0]); cudaFree(kv.second.d_patches[1]); cudaFree(kv.second.d_direct); }
   p->area.clear();
 }
 /* base frames 0/1 of the current config (see tbx_render.cuh), gray and RGBA, on the device */
@@ -287,6 +292,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     AreaRes r;
     r.plan = plan;
     r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0; r.d_patches[0] = r.d_patches[1] = 0;
+    r.d_direct = 0; r.direct_ok = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; b++) {
@@ -299,6 +305,15 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
       CK(cudaMalloc(&r.d_patches[b], patches.size() * sizeof(TbxDigitPatch)));
       CK(cudaMemcpy(r.d_patches[b], patches.data(), patches.size() * sizeof(TbxDigitPatch), cudaMemcpyHostToDevice));
     }
+    if (p->game == TBX_BREAKOUT) {
+      std::vector<TbxBrkDirect> aux(1);
+      tbx::build_brk_direct(p->cfg, p->brk_tables[p->cfg.brk.default_tbl], rs, plan, p->h_base_gray[0].data(), aux[0]);
+      if (aux[0].ok) {
+        CK(cudaMalloc(&r.d_direct, sizeof(TbxBrkDirect)));
+        CK(cudaMemcpy(r.d_direct, aux.data(), sizeof(TbxBrkDirect), cudaMemcpyHostToDevice));
+        r.direct_ok = 1;
+      }
+    }
     it = p->area.insert(std::make_pair(key, r)).first;
   }
   *out = &it->second;
@@ -308,12 +323,8 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
 static int align16(int v) { return (v + 15) & ~15; }
 
 template <int GAME, int MODE, int TX, int TY> static int launch_render(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, cudaStream_t s) {
-  static int configured = 0; /* per instantiation */
-  if (configured < smem) {
-    const int want = smem > 160 * 1024 ? smem : 160 * 1024;
-    CK((cudaFuncSetAttribute(render_kernel<GAME, MODE, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)));
-    configured = want;
-  }
+  /* the opt-in is per device (a process may hold pools on several GPUs): set it on every launch, a cheap host-side call */
+  CK((cudaFuncSetAttribute(render_kernel<GAME, MODE, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 160 * 1024 ? smem : 160 * 1024)));
   const int H = Traits<GAME>::H;
   dim3 grid(blocks(a.n, TBX_EPC), ((MODE == TBX_OBS_GRAY_AREA ? a.out_h : H) + a.band_rows - 1) / a.band_rows);
   /* measured: Breakout's few primitives keep 4 warps busy, the sprite-heavy games use 8 (profiles/r1_native_layouts.md) */
@@ -328,14 +339,10 @@ template <int GAME, int MODE, int TX, int TY> static int launch_render(const Ren
 /* native layouts as broadcast + patch (tbx_render_native.cuh) */
 template <int GAME, int PIX> static int launch_native_pix(const tbx_pool *p, const RenderArgs &a, const void *cfg_host, int band_smem, cudaStream_t s) {
   typedef typename Traits<GAME>::Cfg Cfg;
-  static int configured = 0;
   const int threads = 256;
   const int patch_smem = a.smem_canvas; /* the records of the CTA's 8 envs */
-  if (!configured) {
-    CK((cudaFuncSetAttribute(base_fill_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)));
-    CK((cudaFuncSetAttribute(native_patch_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
-    configured = 1;
-  }
+  CK((cudaFuncSetAttribute(base_fill_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)));
+  CK((cudaFuncSetAttribute(native_patch_kernel<GAME, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
   if (band_smem > 64 * 1024 || patch_smem > 160 * 1024) return set_err(TBX_EINVAL, "frame too wide for the native render path");
   const int H = Traits<GAME>::H;
   dim3 grid(blocks(a.n, TBX_FILL_ENVS), (H + a.band_rows - 1) / a.band_rows);
@@ -359,12 +366,10 @@ static int launch_native(const tbx_pool *p, int mode, const RenderArgs &a, int b
 
 /* INTER_AREA, one warp per env (tbx_render_area.cuh) */
 template <int GAME, int TX, int TY, bool DUAL> static int launch_area_tile_dual(const RenderArgs &a, const void *cfg_host, const TbxAreaPlan *plan_host, int smem, int threads, cudaStream_t s) {
-  static int configured = 0;
-  if (configured < smem) {
-    CK((cudaFuncSetAttribute(area_tile_kernel<GAME, TX, TY, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
-    configured = smem;
-  }
-  area_tile_kernel<GAME, TX, TY, DUAL><<<blocks(a.n, TBX_EPC), threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, *plan_host);
+  CK((cudaFuncSetAttribute(area_tile_kernel<GAME, TX, TY, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+  /* env-list mode (the envs the direct kernel handed over, normally none): a small grid walks the list */
+  const int grid = a.env_list ? (blocks(a.n, TBX_EPC) < 296 ? blocks(a.n, TBX_EPC) : 296) : blocks(a.n, TBX_EPC);
+  area_tile_kernel<GAME, TX, TY, DUAL><<<grid, threads, smem, s>>>(a, *(const typename Traits<GAME>::Cfg *)cfg_host, *plan_host);
   CK(cudaGetLastError());
   return TBX_OK;
 }
@@ -485,6 +490,19 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
         a.warp_bytes = TBX_TILE_LCAP * 20 + 32 + a.tile_bytes * (dual ? 2 : 1);
         const int smem = a.smem_canvas + (threads / 32) * a.warp_bytes;
         cudaStream_t s = (cudaStream_t)stream;
+        /* Direct kernel first (tbx_render_direct.cuh; TBX_AREA_KERNEL=tile turns it off): closed forms for the envs they
+         * cover, the rest are listed and rendered by the tile kernel in env-list mode right after (usually an empty list) */
+        if (ar->direct_ok && !dual && !(ksel && !strcmp(ksel, "tile"))) {
+          if (!p->d_fb) { CK(cudaMalloc(&p->d_fb, ((size_t)p->n_pad + 8) * sizeof(int32_t))); CK(cudaMemsetAsync(p->d_fb, 0, 8 * sizeof(int32_t), s)); }
+          DirectArgs da;
+          da.aux = ar->d_direct; da.fb_list = p->d_fb + 8; da.fb_count = p->d_fb;
+          da.hstride = (out_w + 3) & ~3;
+          da.warp_bytes = align16(TBX_BRK_MAX_ROWS * da.hstride * (int)sizeof(float));
+          const int dsmem = a.smem_canvas + (TBX_DIRECT_THREADS / 32) * da.warp_bytes;
+          CK(tbx_launch_brk_direct(tx, ty, a, p->cfg.brk, ar->plan, da, dsmem, s));
+          a.env_list = p->d_fb + 8;
+          a.env_count = p->d_fb;
+        }
         if (p->game == TBX_BREAKOUT) return launch_area_tile_taps<TBX_BREAKOUT>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
         if (p->game == TBX_AMIDAR) return launch_area_tile_taps<TBX_AMIDAR>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);
         return launch_area_tile_taps<TBX_SPACE_INVADERS>(tx, ty, a, cfg_ptr(p), host_plan, smem, threads, s);

@@ -38,9 +38,9 @@ namespace tbxk {
 #define TBX_MAX_RECTS 96
 #define TBX_MAX_BIG 64 /* queue of large / sprite primitives of a group painted by several warps */
 
-__device__ const uint32_t d_bank[TBX_BANK_WORDS] = TBX_BANK_INIT;
+static __device__ const uint32_t d_bank[TBX_BANK_WORDS] = TBX_BANK_INIT;
 /* ceil(65536 / s) for the sprite scale factors s = 1..15 */
-__device__ const uint32_t d_inv16[16] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370};
+static __device__ const uint32_t d_inv16[16] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370};
 
 template <int GAME> struct Traits;
 template <> struct Traits<TBX_BREAKOUT> {

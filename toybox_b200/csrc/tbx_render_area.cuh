@@ -237,18 +237,24 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
   const TbxAreaPlan *__restrict__ plan = a.plan; /* per-lane indexed reads: global memory / L1 */
   const TbxAreaPlan &cp = plan_c;                /* warp-uniform reads: constant bank */
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
-  const int e0 = blockIdx.x * TBX_EPC;
-  const int ne = min(TBX_EPC, a.n - e0);
   constexpr bool dual = DUAL; /* observation = down-sample of max(frame of planes, frame of planes2): a.planes2 != NULL */
   uint32_t *recs2 = recs + RW * TBX_EPC;
+  /* env-list mode (a.env_list != NULL: the envs the direct kernel of tbx_render_direct.cuh handed over): a small grid
+   * walks the list chunk by chunk; otherwise CTA b renders envs 8b .. 8b+7 and the loop runs once */
+  const int n_total = a.env_count ? *a.env_count : a.n;
+  for (int chunk = blockIdx.x; chunk * TBX_EPC < n_total; chunk += gridDim.x) {
+  const int e0 = chunk * TBX_EPC;
+  const int ne = min(TBX_EPC, n_total - e0);
+  if (chunk != (int)blockIdx.x) __syncthreads(); /* every warp is done with the previous chunk's records */
   for (int i = tid; i < RW * TBX_EPC; i += blockDim.x) {
     const int w = i / TBX_EPC, j = i - w * TBX_EPC;
     if (j < ne) {
-      recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
-      if (dual) recs2[j * RW + w] = a.planes2[(size_t)w * a.n_pad + e0 + j];
+      const int env = a.env_list ? a.env_list[e0 + j] : e0 + j;
+      recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + env];
+      if (dual) recs2[j * RW + w] = a.planes2[(size_t)w * a.n_pad + env];
     }
   }
-  __syncthreads(); /* the only CTA barrier: from here on every warp works alone */
+  __syncthreads(); /* the only CTA barrier per chunk: from here on every warp works alone */
 
   uint8_t *wmem = smem + a.smem_canvas + wid * a.warp_bytes;
   uint4 *list = reinterpret_cast<uint4 *>(wmem);
@@ -269,7 +275,8 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
     const int base2 = dual ? T::base_id(R2, cfg, tables) : base;
     const uint8_t *bfr2 = base2 ? a.base[1] : a.base[0];
     const bool redo_all = base2 != base; /* the two frames differ everywhere the base frames do: recompute every tile */
-    uint8_t *out = a.dst + (size_t)(e0 + j) * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
+    const int env = a.env_list ? a.env_list[e0 + j] : e0 + j;
+    uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
     { /* 1. the static part of the frame */
       const uint8_t *src = base ? a.base_out[1] : a.base_out[0];
       const int nb = dw * dh;
@@ -543,9 +550,9 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
       }
     }
     /* FrameStack.reset (atari_wrappers.py:262-266): a reset observation fills every slot of the env's ring */
-    if (a.reset_flags && a.stack_k > 1 && a.reset_flags[e0 + j]) {
+    if (a.reset_flags && a.stack_k > 1 && a.reset_flags[env]) {
       __syncwarp();
-      uint8_t *ring = a.dst + (size_t)(e0 + j) * a.env_stride;
+      uint8_t *ring = a.dst + (size_t)env * a.env_stride;
       const int nb = dw * dh;
       for (int k = 0; k < a.stack_k; k++) {
         if (k == a.stack_slot) continue;
@@ -557,6 +564,13 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
         }
       }
     }
+  }
+  } /* chunk */
+  /* env-list mode: the last CTA to finish empties the list for the next render (every CTA has read the count by then) */
+  if (a.env_list && a.env_count && tid == 0) {
+    int *cnt = const_cast<int *>(a.env_count);
+    __threadfence();
+    if (atomicAdd(cnt + 1, 1) == (int)gridDim.x - 1) { cnt[0] = 0; cnt[1] = 0; __threadfence(); }
   }
 }
 
