@@ -42,7 +42,13 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--policy", default="random", choices=["random", "track"],
                     help="random = the headline uniform stream; track = scripted Breakout ball tracking (breaks bricks)")
-    ap.add_argument("--presteps", type=int, default=0, help="untimed step-only frames before the warm-up")
+    ap.add_argument("--presteps", type=int, default=2000,
+                    help="untimed step-only frames before the warm-up (default 2000: a steady-state pool whose episodes end and restart)")
+    ap.add_argument("--no-protocol", action="store_true", help="skip the canonical-protocol repeats (warm-up 100, 5 x T steps)")
+    ap.add_argument("--protocol-steps", type=int, default=1000, help="T of the canonical protocol (SURVEY 8d)")
+    ap.add_argument("--no-states", dest="states", action="store_false", help="skip the fresh-game / mid-game sub-records")
+    ap.add_argument("--interventions", action="store_true",
+                    help="supplementary line: BASELINE configs[3] -- every 64 steps export the state JSON of 1,024 random envs, mutate, import")
     ap.add_argument("--mixed", type=int, default=0, metavar="TOTAL_ENVS",
                     help="supplementary line: BASELINE configs[4] -- TOTAL_ENVS (e.g. 1048576) split 1/3 per game and evenly over the GPUs, "
                          "gray84, NCCL all-reduce of the episode statistics every 256 steps")
@@ -293,6 +299,15 @@ def mixed_arm(args):
         dist.destroy_process_group()
 
 
+def _sem(xs):
+    n = len(xs)
+    m = sum(xs) / n
+    if n < 2:
+        return m, 0.0
+    var = sum((x - m) ** 2 for x in xs) / (n - 1)
+    return m, (var / n) ** 0.5
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -303,6 +318,9 @@ def main():
         return
     if args.wrapped:
         wrapped_arm(args)
+        return
+    if args.interventions:
+        interventions_arm(args)
         return
     import numpy as np
     import torch
@@ -318,48 +336,95 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    n = args.envs
-    env0 = rank * n
-    pool = toybox_b200.BatchedToybox(args.game, n, device=dev, obs=args.obs,
-                                     seeds=(1234 + env0 + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF)
-    fb = obs_bytes(args.game, args.obs)
-    obs = torch.empty((n,) + pool.obs_shape, dtype=torch.uint8, device=dev)
-    actions = torch.empty(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
-
-    def fill(t):
-        if args.policy == "track":
-            pool.fill_policy_actions(actions, 1, t)
-        else:
-            pool.fill_random_actions(actions, ACTION_SEED, t, env0)
-
-    def step(t, ev=None):
-        fill(t)
-        if ev is not None:
-            ev[0].record(stream)
-        pool.apply_ale_action(actions, auto_reset=True)
-        if ev is not None:
-            ev[1].record(stream)
-        pool.render(out=obs)
-        if ev is not None:
-            ev[2].record(stream)
-
-    t = 0
-    for _ in range(args.presteps):          # advance the games without rendering (untimed) to reach mid-game states
-        fill(t)
-        pool.apply_ale_action(actions, auto_reset=True)
-        t += 1
-    for _ in range(max(args.warmup, 3)):
-        step(t)
-        t += 1
-    torch.cuda.synchronize(dev)
+    fb = obs_bytes(args.game, args.obs)
+    rec_bytes = 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- timed region: exactly K steps, device-timed, max over ranks
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    class Rollout:
+        """one pool + its buffers + the benchmark's step (fill actions, step, render)"""
+
+        def __init__(self, n, policy="random"):
+            self.n, self.policy, self.env0, self.t = n, policy, rank * n, 0
+            self.pool = toybox_b200.BatchedToybox(args.game, n, device=dev, obs=args.obs,
+                                                  seeds=(1234 + self.env0 + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF)
+            self.obs = torch.empty((n,) + self.pool.obs_shape, dtype=torch.uint8, device=dev)
+            self.actions = torch.empty(n, dtype=torch.int32, device=dev)
+
+        def fill(self):
+            if self.policy == "track":
+                self.pool.fill_policy_actions(self.actions, 1, self.t)
+            else:
+                self.pool.fill_random_actions(self.actions, ACTION_SEED, self.t, self.env0)
+
+        def step(self, ev=None, render=True):
+            self.fill()
+            if ev is not None:
+                ev[0].record(stream)
+            self.pool.apply_ale_action(self.actions, auto_reset=True)
+            if ev is not None:
+                ev[1].record(stream)
+            if render:
+                self.pool.render(out=self.obs)
+            if ev is not None:
+                ev[2].record(stream)
+            self.t += 1
+
+        def presteps(self, k):           # advance the games without rendering (untimed)
+            for _ in range(k):
+                self.step(render=False)
+
+        def timed(self, k, split=False):
+            """k steps between two events on the launching stream; returns (ms, step_ms, render_ms)"""
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)] if split else None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(k):
+                self.step(evs[i] if split else None)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            if not split:
+                return ms, None, None
+            return ms, sum(e[0].elapsed_time(e[1]) for e in evs) / k, sum(e[1].elapsed_time(e[2]) for e in evs) / k
+
+        def close(self):
+            self.pool.close()
+
+    n = args.envs
+    ro = Rollout(n, args.policy)
+    pool = ro.pool
+    ro.presteps(args.presteps)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        ro.step()
+    torch.cuda.synchronize(dev)
+
+    # ---- the path's one collective, device side: the episode-statistics vector, summed / maxed over the GPUs by NCCL.  It
+    # runs INSIDE the timed region (once, after the K-th step) and is timed on its own below.
+    stats_dev = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def reduce_stats():
+        pool.episode_stats_into(stats_dev)
+        if dist is not None:
+            mx = stats_dev[3:].clone()
+            dist.all_reduce(stats_dev, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            stats_dev[3:] = mx
+
+    reduce_stats()
+    # ---- timed region: exactly K steps (+ the statistics reduce), device-timed, max over ranks
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     sampler = ClockSampler(local)
@@ -369,30 +434,49 @@ def main():
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
     for k in range(K):
-        step(t, evs[k])
-        t += 1
+        ro.step(evs[k])
+    reduce_stats()
     e_end.record(stream)
     barrier()
-    ms = e_start.elapsed_time(e_end)
-    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e_start.elapsed_time(e_end))
     step_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
     pool.check()
-    if dist is not None:
-        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-        # the path's one collective: the episode-statistics vector (tens of bytes), summed / maxed over GPUs
-        st = torch.tensor(pool.episode_stats(), dtype=torch.int64, device=dev)
-        mx = st[3:].clone()
-        dist.all_reduce(st, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        stats = [int(st[0]), int(st[1]), int(st[2]), int(mx[0])]
-    else:
-        stats = pool.episode_stats()
     value = world * n * K / (ms * 1e-3)
+    stats = [int(v) for v in stats_dev.cpu()]
 
-    # ---- e2e: the same metric through the host-facing call (host actions in, host observations out)
+    # ---- the survey's protocol (after test/benchmark.py:119-166): warm-up 100, T = 1,000 timed steps, best of 5 and
+    # mean +- SEM over the 5 repeats -- measured in the same run, after the driver's K-step region above
+    protocol = None
+    if not args.no_protocol:
+        T, reps = args.protocol_steps, 5
+        for _ in range(100):
+            ro.step()
+        vals = []
+        for _ in range(reps):
+            barrier()
+            pms = max_over_ranks(ro.timed(T)[0])
+            vals.append(world * n * T / (pms * 1e-3))
+        mean, sem = _sem(vals)
+        protocol = {"warmup": 100, "steps": T, "repeats": reps, "best": max(vals), "mean": mean, "sem": sem, "unit": "env-steps/s",
+                    "note": "canonical protocol of SURVEY 8d; `value` above is the driver's --steps/--warmup region"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the collective on its own: 20 statistics reduces back to back
+    collective = None
+    if dist is not None:
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(20):
+            reduce_stats()
+        c1.record(stream)
+        barrier()
+        collective = {"op": "NCCL all_reduce of [episodes, sum_return, sum_length | max_return] int64", "us": max_over_ranks(c0.elapsed_time(c1)) * 1e3 / 20,
+                      "inside_timed_region": True}
+
+    # ---- e2e: the same metric through the host-facing call (host actions in, host observations out), with its own
+    # roofline: a bare pinned device->host copy of the same bytes, timed on every rank at the same time
     e2e = None
     if not args.no_e2e:
         rng = np.random.default_rng(rank)
@@ -407,21 +491,64 @@ def main():
         for _ in range(ke):
             pool.step_host(h_actions, obs_out=h_obs)
         barrier()
-        sec = time.perf_counter() - t0
-        if dist is not None:
-            tt = torch.tensor([sec], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            sec = float(tt.item())
-        e2e = {"value": world * n * ke / sec, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
-               "d2h_bytes_per_step": n * (fb + 4 + 1 + 4 + 4), "steps": ke,
-               "api": "BatchedToybox.step_host -> tbx_step_host (pinned host actions in; obs, reward, done, score, lives out)"}
+        sec = max_over_ranks(time.perf_counter() - t0)
+        d2h = n * (fb + 4 + 1 + 4 + 4)
+        for _ in range(2):
+            h_obs.copy_(ro.obs, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            h_obs.copy_(ro.obs, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        barrier()
+        csec = max_over_ranks(time.perf_counter() - t0)
+        pcie = n * fb * ke / csec / 1e9
+        e2e = {"value": world * n * ke / sec, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h, "steps": ke,
+               "api": "BatchedToybox.step_host -> tbx_step_host (pinned host actions in; obs, reward, done, score, lives out)",
+               "pcie_gbs": pcie, "achieved_gbs": d2h * ke / sec / 1e9, "frac": (d2h * ke / sec / 1e9) / pcie,
+               "pcie_note": "pcie_gbs = a bare pinned cudaMemcpyAsync D2H of the observation bytes per rank, all %d rank(s) copying at the "
+                            "same time: the host-side ceiling of this call" % world}
+        del h_obs
+
+    # ---- the same pool from other game states, as named sub-records (the render cost follows what differs from a fresh game)
+    states = {}
+    if args.states and args.game == "breakout" and args.obs == "gray84":
+        def sub(name, policy, pre):
+            r2 = Rollout(n, policy)
+            r2.presteps(pre)
+            for _ in range(5):
+                r2.step()
+            torch.cuda.synchronize(dev)
+            barrier()
+            sms, s_ms, r_ms = r2.timed(50, split=True)
+            sms = max_over_ranks(sms)
+            est = r2.pool.episode_stats()
+            r2.close()
+            states[name] = {"value": world * n * 50 / (sms * 1e-3), "unit": "env-steps/s", "steps": 50, "policy": policy, "presteps": pre,
+                            "render_ms": r_ms, "step_ms": s_ms, "episodes": est[0]}
+        sub("fresh_game", "random", 0)
+        sub("midgame_tracking_policy_3000", "track", 3000)
+
+    # ---- north_star: Breakout gray84 at batch 1M over 8 GPUs = 131,072 envs per GPU (the weak-scaling line above keeps --envs)
+    north_star = None
+    if world == 8 and args.game == "breakout" and args.obs == "gray84" and args.policy == "random":
+        ro.close()
+        r3 = Rollout(131072, "random")
+        r3.presteps(args.presteps)
+        for _ in range(W):
+            r3.step()
+        barrier()
+        nms = max_over_ranks(r3.timed(max(K, 50))[0])
+        north_star = {"value": world * 131072 * max(K, 50) / (nms * 1e-3), "unit": "env-steps/s", "total_envs": world * 131072,
+                      "envs_per_gpu": 131072, "steps": max(K, 50), "presteps": args.presteps, "target": 1e9}
+        ro = r3
+        pool = ro.pool
 
     # ---- the HBM-bound layout of the same render path (native RGBA frames), same pool and states: supplementary roofline
     native = None
-    if rank == 0 and args.obs == "gray84":
+    if rank == 0 and args.obs == "gray84" and north_star is None:
         nb = obs_bytes(args.game, "rgba")
-        nn = min(n, (24 << 30) // nb)                      # output buffer of at most 24 GiB
-        if nn == n:
+        if n * nb <= (24 << 30):
             big = torch.empty((n, nb), dtype=torch.uint8, device=dev)
             for _ in range(3):
                 pool.render(out=big, obs="rgba")
@@ -433,7 +560,7 @@ def main():
             ev[1].record(stream)
             torch.cuda.synchronize(dev)
             nms = ev[0].elapsed_time(ev[1]) / 10
-            nbytes = n * (nb + 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game])
+            nbytes = n * (nb + rec_bytes)
             native = {"kernel": "base_fill_kernel + native_patch_kernel<%s,rgba>" % args.game, "launch_ms": nms, "bytes_per_launch": nbytes,
                       "achieved": nbytes / (nms * 1e-3) / 1e9, "unit": "GB/s", "frames_per_sec": n / (nms * 1e-3)}
             del big
@@ -443,7 +570,6 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (render): algorithmic bytes per launch / measured launch time
-    rec_bytes = 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game]
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -451,12 +577,15 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = n * (fb + rec_bytes)          # frame written + state record read, per env, per launch
     achieved = alg_bytes / (render_ms * 1e-3) / 1e9
-    kname = ("area_tile_kernel<%s>" if args.obs == "gray84" else "render_kernel<%s," + args.obs + ">") % args.game
+    if args.obs == "gray84":
+        kname = "brk_direct_kernel" if args.game == "breakout" and os.environ.get("TBX_AREA_KERNEL") not in ("tile", "cta") else "area_tile_kernel<%s>" % args.game
+    else:
+        kname = "base_fill_kernel + native_patch_kernel<%s,%s>" % (args.game, args.obs)
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the committed
-    # `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py); null when never captured
+    # `ncu --set full` capture (profiles/r2_traffic.json, written by tools/ncu_traffic.py); null when never captured
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         key = "%s/%s/%d" % (args.game, args.obs, n)
         if key in tr:
             traffic = tr[key]["dram_bytes"]
@@ -465,7 +594,7 @@ def main():
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": alg_bytes, "launch_ms": render_ms, "step_kernel_ms": step_ms,
-                "note": "a 7 KB gray84 frame costs more instruction issue than DRAM time; the HBM-bound layout is in roofline_native"}
+                "note": "a 7 KB gray84 frame costs more instruction issue than DRAM time; the HBM-bound layout is in roofline.native"}
     if native is not None:
         native["frac"] = native["achieved"] / peak
     roofline["native"] = native
@@ -478,18 +607,21 @@ def main():
         v, s = cpu_rollout(args.game, args.obs, n_cpu, steps_cpu, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": "%d envs x %d frames (step + %s render), %.1f s, oracle/ C restatement with OpenMP" % (n_cpu, steps_cpu, args.obs, s)}
+    launches = ["fill_actions_kernel", "step_kernel", kname] + (["area_tile_kernel (env-list mode, normally empty)"] if kname == "brk_direct_kernel" else [])
     line = {
         "metric": "env-steps/sec with rendered frames", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": GAME_DTYPE[args.game], "data": "synthetic",
         "config": {"workload": workload_name(args.game, n, args.obs), "envs_per_gpu": n, "obs_bytes_per_env": fb,
                    "l2": "each step writes %d MB of observations (> 126 MB L2) between reuses of the %d MB state" %
                          (n * fb // 2 ** 20, n * rec_bytes // 2 ** 20),
                    "seeds": "env i: set_seed(1234+i); actions: counter-based stream seed 0xB200",
-                   "policy": args.policy, "presteps": args.presteps},
-        "frames_per_sec": value, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
-        "launches_per_step": ["fill_actions_kernel", "step_kernel", "render_kernel"],
-        "clocks": clocks, "episode_stats": {"episodes": stats[0], "sum_return": stats[1], "sum_length": stats[2], "max_return": stats[3]},
+                   "policy": args.policy, "presteps": args.presteps,
+                   "state": "steady state: %d untimed step-only frames before the warm-up, episodes end and auto-reset inside the run" % args.presteps},
+        "frames_per_sec": value, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": len(launches) * K,
+        "launches_per_step": launches, "protocol": protocol, "states": states or None, "collective": collective, "north_star_1M": north_star,
+        "clocks": clocks, "episode_stats": {"episodes": stats[0], "sum_return": stats[1], "sum_length": stats[2], "max_return": stats[3],
+                                            "scope": "all ranks (NCCL-reduced), since pool creation"},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

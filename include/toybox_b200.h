@@ -116,6 +116,9 @@ void tbx_free_str(char *s);
  * baselines/baselines/bench/monitor.py:58-76): out_host[0..3] = episodes finished, sum of episode returns,
  * sum of episode lengths, max episode return.  This 32-byte vector is what the multi-GPU driver all-reduces. */
 int tbx_stats_read(tbx_pool *pool, int64_t *out_host, int reset, void *stream);
+/* The same vector copied device-to-device into out_dev (int64[4]) in stream order, no host synchronisation: the form the
+ * NCCL all-reduce of a multi-GPU rollout consumes (toybox_b200/distributed.py, bench.py). */
+int tbx_stats_read_device(tbx_pool *pool, int64_t *out_dev, void *stream);
 
 /* The synthetic random-action stream of the benchmark and parity tests: fills actions_dev[i] with
  * legal[index(seed, env0 + i, t)] for the pool's game (counter-based, reproducible on the CPU). */

@@ -220,7 +220,7 @@ int emu_render_direct(Emu *e, int out_w, int out_h, uint8_t *out) {
   TbxMover mv[BRK_N_MOVERS];
   int fx0[BRK_N_MOVERS], fx1[BRK_N_MOVERS], fy0[BRK_N_MOVERS], fy1[BRK_N_MOVERS];
   for (int m = 0; m < BRK_N_MOVERS; m++) {
-    mv[m] = brk_mover(R, e->cfg.brk, A, m);
+    mv[m] = brk_mover(R, e->cfg.brk, A.paddle_gray, A.ball_gray, m);
     if (mv[m].x0 >= mv[m].x1) continue;
     fx0[m] = pl.xdlo[mv[m].x0]; fx1[m] = pl.xdhi[mv[m].x1 - 1]; fy0[m] = pl.ydlo[mv[m].y0]; fy1[m] = pl.ydhi[mv[m].y1 - 1];
     if (fy0[m] <= A.hud_dyhi) return 1;

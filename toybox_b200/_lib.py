@@ -3,6 +3,7 @@
 callers raise."""
 import ctypes as C
 import os
+import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -11,26 +12,47 @@ _CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off"]
 SOURCES = ["tbx_pool.cu", "tbx_direct.cu", "tbx_host.cpp"]
+_OBJ = os.path.join(_HERE, "build")
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
 
 
-def _stale():
-    if not os.path.exists(_SO):
-        return True
-    t = os.path.getmtime(_SO)
-    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "toybox_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+def _deps(path, seen=None):
+    """`path` and every local header it includes, transitively (quoted includes only)."""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in _INC.findall(open(path).read()):
+        _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
+def _newer(target, deps):
+    return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
 
 
 def build(force=False, verbose=False):
-    """Compile toybox_b200/libtoybox_b200.so for sm_100a (cross-compiles without a GPU)."""
-    if not force and not _stale():
-        return _SO
+    """Compile toybox_b200/libtoybox_b200.so for sm_100a (cross-compiles without a GPU): one object per translation unit
+    under toybox_b200/build/, rebuilt only when the unit or a header it includes changed, compiled in parallel."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TBX_NVCC_EXTRA", "").split()          # tuning experiments, e.g. -DTBX_RENDER_THREADS=128
-    cmd = [nvcc, "-t", "0"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + [os.path.join(_CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    os.makedirs(_OBJ, exist_ok=True)
+    jobs, objs = [], []
+    for src in SOURCES:
+        path = os.path.join(_CSRC, src)
+        obj = os.path.join(_OBJ, os.path.splitext(src)[0] + (".tuned.o" if extra else ".o"))
+        objs.append(obj)
+        if force or extra or _newer(obj, _deps(path)):
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            jobs.append(subprocess.Popen(cmd))
+    for j in jobs:
+        if j.wait() != 0:
+            raise subprocess.CalledProcessError(j.returncode, j.args)
+    if jobs or _newer(_SO, objs):
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", _SO] + objs)
     return _SO
 
 
@@ -75,6 +97,7 @@ def lib():
         "tbx_query_json": (i32, [vp, i32, cp, cp, C.POINTER(vp)]),
         "tbx_free_str": (None, [vp]),
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
+        "tbx_stats_read_device": (i32, [vp, vp, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
         "tbx_fill_actions_at": (i32, [vp, vp, u64, u64, vp, vp]),
         "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
@@ -98,7 +121,7 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
            "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy",
-           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set", "tbx_fill_actions_at"]
+           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set", "tbx_fill_actions_at", "tbx_stats_read_device"]
 
 
 def check(rc):

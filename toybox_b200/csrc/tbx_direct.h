@@ -28,7 +28,7 @@ struct TbxMover { int x0, y0, x1, y1; uint32_t gray; };
 /* ------------------------------------------------------------------ Breakout */
 #define TBX_BD_MAX_STATIC 16
 #define BRK_N_MOVERS (1 + TBX_BRK_MAX_BALLS) /* paddle, balls in draw order */
-typedef struct {
+typedef struct TbxBrkDirect {
   int32_t ok;                    /* 0: this (config, output size) pair is rendered by the tile kernel */
   int32_t ncols, nrows;          /* the default table is a grid of ncols x nrows bricks, index = col * nrows + row */
   int32_t wx0, wy0, bw, bh;      /* origin of the grid and brick size in pixels */
@@ -43,13 +43,14 @@ typedef struct {
   uint8_t hsel[TBX_AREA_MAX_DST][TBX_AREA_MAX_TAPS]; /* per output row and tap: H row -- < nrows: brick row, else static row (- nrows) */
   uint32_t wordcols[32];          /* per output word (4 columns): mask of the brick columns that feed it */
   uint8_t brickgray[TBX_BRK_MAX_BRICKS];
-  float hlut[TBX_BRK_MAX_ROWS][4][TBX_AREA_MAX_DST];  /* [brick row][alive(col0) | alive(col0 + 1) << 1][dx] */
-  float hstatic[TBX_BD_MAX_STATIC][TBX_AREA_MAX_DST]; /* horizontal sums of the base-frame-0 rows around the wall */
+  uint32_t inv32[TBX_AREA_MAX_DST + 1]; /* ceil(2^32 / n) for n >= 2: i / n == umulhi(i, inv32[n]) for the small i used here */
+  alignas(16) float hlut[TBX_BRK_MAX_ROWS][4][TBX_AREA_MAX_DST];  /* [brick row][alive(col0) | alive(col0 + 1) << 1][dx] */
+  alignas(16) float hstatic[TBX_BD_MAX_STATIC][TBX_AREA_MAX_DST]; /* horizontal sums of the base-frame-0 rows around the wall */
 } TbxBrkDirect;
 
 /* paddle (m == 0) or ball m - 1 as a clipped rectangle */
-TBX_HD TbxMover brk_mover(const uint32_t *R, const BrkCfg &c, const TbxBrkDirect &A, int m) {
-  TbxMover v; v.x0 = v.y0 = v.x1 = v.y1 = 0; v.gray = m == 0 ? A.paddle_gray : A.ball_gray;
+TBX_HD TbxMover brk_mover(const uint32_t *R, const BrkCfg &c, uint32_t paddle_gray, uint32_t ball_gray, int m) {
+  TbxMover v; v.x0 = v.y0 = v.x1 = v.y1 = 0; v.gray = m == 0 ? paddle_gray : ball_gray;
   if (m < 0 || m >= BRK_N_MOVERS) return v;
   const TbxPrim p = brk_prim(R, c, (const BrkTable *)0, m == 0 ? BRK_SLOT_PADDLE : BRK_SLOT_BALLS + m - 1); /* these slots never read the tables */
   if (p.h <= 0) return v;
@@ -137,7 +138,7 @@ TBX_HD uint8_t brk_direct_wall_pixel(const TbxBrkDirect &A, const TbxAreaPlan &p
 /* HUD digit k (0 = least significant) of a field value: -1 = not shown (tbx_prim_digit) */
 TBX_HD int tbx_digit_at(int value, int k) {
   uint32_t q = value < 0 ? 0u : (uint32_t)value;
-  for (int i = 0; i < k; i++) q /= 10u;
+  for (int i = 0; i < k && q; i++) q /= 10u;
   if (k > 0 && q == 0) return -1;
   return (int)(q % 10u);
 }

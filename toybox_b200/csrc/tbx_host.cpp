@@ -4,6 +4,7 @@
 #include "tbx_breakout.h"
 #include "tbx_space_invaders.h"
 #include "tbx_amidar.h"
+#include "tbx_direct.h"
 #include <errno.h>
 #include <math.h>
 #include <string.h>
@@ -959,6 +960,7 @@ void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, c
   }
   A.ncols = ncols; A.nrows = nrows; A.wx0 = wx0; A.wy0 = wy0; A.bw = bw; A.bh = bh;
   A.paddle_gray = tbx_luma(c.brk.paddle_color); A.ball_gray = tbx_luma(c.brk.ball_color);
+  for (int k = 2; k <= TBX_AREA_MAX_DST; k++) A.inv32[k] = 0xffffffffu / (uint32_t)k + 1u;
   memset(A.xcol, 255, sizeof A.xcol);
   memset(A.yrow, 255, sizeof A.yrow);
   for (int x = wx0; x < wx0 + ncols * bw; x++) A.xcol[x] = (uint8_t)((x - wx0) / bw);

@@ -5,10 +5,11 @@
 #ifndef TBX_HOST_H
 #define TBX_HOST_H
 #include "tbx_records.h"
-#include "tbx_direct.h"
 #include "tbx_json.h"
 #include <string>
 #include <vector>
+
+struct TbxBrkDirect; /* tbx_direct.h */
 
 namespace tbx {
 

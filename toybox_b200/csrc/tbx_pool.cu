@@ -8,6 +8,8 @@
 #include <new>
 #include <string>
 #include <string.h>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 using namespace tbxk;
@@ -47,12 +49,31 @@ struct tbx_pool {
   std::map<std::pair<int, int>, struct AreaRes> area;
   int32_t *d_dense; /* [0] = count, [8..] = env ids the patch kernel left to the canvas kernel */
   int32_t *d_fb;    /* [0] = count, [1] = finished CTAs, [8..] = env ids the direct INTER_AREA kernel left to the tile kernel */
+  /* JSON import / export staging (grown on demand, kept): env ids and AoS records on the device, records in pinned host memory */
+  int32_t *j_ids; uint32_t *j_recs, *j_host; size_t j_cap_ids, j_cap_words;
   /* tbx_step_host staging */
   cudaStream_t hs;
   int32_t *h_actions_dev, *h_reward_dev, *h_score_dev, *h_lives_dev;
   uint8_t *h_done_dev, *h_obs_dev;
   size_t h_obs_cap;
 };
+
+/* The JSON codec is host work per env (build / walk a document tree, print / parse ~20-40 KB of text): spread the envs of a
+ * batched call over host threads.  f(i) may throw; the first message is re-thrown on the calling thread. */
+template <class F> static void parallel_for(int n, F f) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (const char *env = getenv("TBX_JSON_THREADS")) nt = atoi(env);
+  nt = std::max(1, std::min(std::min(nt, 32), n / 8));
+  if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+  std::vector<std::string> errs(nt);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      try { for (int i = t; i < n; i += nt) f(i); } catch (const std::exception &e) { errs[t] = e.what(); if (errs[t].empty()) errs[t] = "error"; }
+    });
+  for (auto &x : th) x.join();
+  for (auto &e : errs) if (!e.empty()) throw std::runtime_error(e);
+}
 
 static size_t cfg_bytes(int game) { return game == TBX_BREAKOUT ? sizeof(BrkCfg) : game == TBX_AMIDAR ? sizeof(AmiCfg) : sizeof(SiCfg); }
 static const void *cfg_ptr(const tbx_pool *p) {
@@ -112,7 +133,7 @@ int tbx_pool_destroy(tbx_pool *p) {
   if (!p) return TBX_OK;
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
-  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal); cudaFree(p->d_dense); cudaFree(p->d_fb);
+  cudaFree(p->d_cfg); cudaFree(p->d_tables); cudaFree(p->planes); cudaFree(p->d_stats); cudaFree(p->d_bad); cudaFree(p->d_legal); cudaFree(p->d_dense); cudaFree(p->d_fb); cudaFree(p->j_ids); cudaFree(p->j_recs); cudaFreeHost(p->j_host);
   drop_render_cache(p);
   cudaFree(p->h_actions_dev); cudaFree(p->h_reward_dev); cudaFree(p->h_score_dev); cudaFree(p->h_lives_dev); cudaFree(p->h_done_dev); cudaFree(p->h_obs_dev);
   if (p->hs) cudaStreamDestroy(p->hs);
@@ -134,7 +155,7 @@ int tbx_pool_create(const char *game, int n_envs, int device, const char *cfg_js
   if (!p) return set_err(TBX_ENOMEM, "out of host memory");
   p->game = g; p->n = n_envs; p->n_pad = (n_envs + 31) & ~31; p->device = device; p->info = tbx::game_info(g);
   p->d_cfg = p->d_tables = 0; p->d_base_gray[0] = p->d_base_gray[1] = p->d_base_rgba[0] = p->d_base_rgba[1] = p->d_base_rgb[0] = p->d_base_rgb[1] = 0; p->d_tables_n = 0; p->planes = 0; p->d_stats = 0; p->d_bad = 0; p->d_legal = 0;
-  p->hs = 0; p->d_dense = 0; p->d_fb = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
+  p->hs = 0; p->d_dense = 0; p->d_fb = 0; p->j_ids = 0; p->j_recs = p->j_host = 0; p->j_cap_ids = p->j_cap_words = 0; p->h_actions_dev = p->h_reward_dev = p->h_score_dev = p->h_lives_dev = 0; p->h_done_dev = p->h_obs_dev = 0; p->h_obs_cap = 0;
   int rc = TBX_OK;
   try {
     tbx::default_config(g, p->cfg);
@@ -269,7 +290,8 @@ static int ensure_base(tbx_pool *p) {
     p->h_base_gray[b].resize(npix);
     tbx::build_base_frame(p->cfg, brk_default, b, p->h_base_rgba[b].data());
     tbx::frame_to_gray(p->h_base_rgba[b].data(), npix, p->h_base_gray[b].data());
-    CK(cudaMalloc(&p->d_base_gray[b], npix));
+    CK(cudaMalloc(&p->d_base_gray[b], npix + 16)); /* slack: the direct kernel reads whole words around a pixel */
+    CK(cudaMemset(p->d_base_gray[b] + npix, 0, 16));
     CK(cudaMalloc(&p->d_base_rgba[b], (size_t)npix * 4));
     CK(cudaMemcpy(p->d_base_gray[b], p->h_base_gray[b].data(), npix, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_base_rgba[b], p->h_base_rgba[b].data(), (size_t)npix * 4, cudaMemcpyHostToDevice));
@@ -305,15 +327,8 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
       CK(cudaMalloc(&r.d_patches[b], patches.size() * sizeof(TbxDigitPatch)));
       CK(cudaMemcpy(r.d_patches[b], patches.data(), patches.size() * sizeof(TbxDigitPatch), cudaMemcpyHostToDevice));
     }
-    if (p->game == TBX_BREAKOUT) {
-      std::vector<TbxBrkDirect> aux(1);
-      tbx::build_brk_direct(p->cfg, p->brk_tables[p->cfg.brk.default_tbl], rs, plan, p->h_base_gray[0].data(), aux[0]);
-      if (aux[0].ok) {
-        CK(cudaMalloc(&r.d_direct, sizeof(TbxBrkDirect)));
-        CK(cudaMemcpy(r.d_direct, aux.data(), sizeof(TbxBrkDirect), cudaMemcpyHostToDevice));
-        r.direct_ok = 1;
-      }
-    }
+    CK(tbx_direct_build(p->cfg, p->game == TBX_BREAKOUT ? &p->brk_tables[p->cfg.brk.default_tbl] : 0, rs, plan, p->h_base_gray[0].data(), &r.d_direct));
+    r.direct_ok = r.d_direct != 0;
     it = p->area.insert(std::make_pair(key, r)).first;
   }
   *out = &it->second;
@@ -496,10 +511,8 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
           if (!p->d_fb) { CK(cudaMalloc(&p->d_fb, ((size_t)p->n_pad + 8) * sizeof(int32_t))); CK(cudaMemsetAsync(p->d_fb, 0, 8 * sizeof(int32_t), s)); }
           DirectArgs da;
           da.aux = ar->d_direct; da.fb_list = p->d_fb + 8; da.fb_count = p->d_fb;
-          da.hstride = (out_w + 3) & ~3;
-          da.warp_bytes = align16(TBX_BRK_MAX_ROWS * da.hstride * (int)sizeof(float));
-          const int dsmem = a.smem_canvas + (TBX_DIRECT_THREADS / 32) * da.warp_bytes;
-          CK(tbx_launch_brk_direct(tx, ty, a, p->cfg.brk, ar->plan, da, dsmem, s));
+          tbx_direct_geometry(p->game, out_w, out_h, da);
+          CK(tbx_launch_direct(p->game, tx, ty, a, cfg_ptr(p), ar->plan, da, s));
           a.env_list = p->d_fb + 8;
           a.env_count = p->d_fb;
         }
@@ -728,6 +741,13 @@ int tbx_stats_read(tbx_pool *p, int64_t *out, int reset, void *stream) {
   return TBX_OK;
 }
 
+int tbx_stats_read_device(tbx_pool *p, int64_t *out_dev, void *stream) {
+  if (!p || !out_dev) return set_err(TBX_EINVAL, "pool/out is NULL");
+  CK(cudaSetDevice(p->device));
+  CK(cudaMemcpyAsync(out_dev, p->d_stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TBX_OK;
+}
+
 int tbx_step_host(tbx_pool *p, const int32_t *actions, int auto_reset, int mode, int out_w, int out_h, uint8_t *obs, int32_t *reward,
                   uint8_t *done, int32_t *score, int32_t *lives) {
   if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
@@ -777,35 +797,46 @@ static char *dup_str(const std::string &s) {
 }
 void tbx_free_str(char *s) { free(s); }
 
-static int fetch_records(tbx_pool *p, const int32_t *ids, int n, std::vector<uint32_t> &recs) {
-  const int rw = p->info->rec_words;
-  for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= p->n) return set_err(TBX_EINVAL, "env id out of range");
-  recs.resize((size_t)n * rw);
-  int32_t *d_ids = 0;
-  uint32_t *d_recs = 0;
-  CK(cudaSetDevice(p->device));
-  CK(cudaDeviceSynchronize());
-  CK(cudaMalloc(&d_ids, n * sizeof(int32_t)));
-  CK(cudaMalloc(&d_recs, recs.size() * 4));
-  CK(cudaMemcpy(d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice));
-  gather_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, d_ids, n, rw, d_recs);
-  CK(cudaGetLastError());
-  CK(cudaMemcpy(recs.data(), d_recs, recs.size() * 4, cudaMemcpyDeviceToHost));
-  cudaFree(d_ids); cudaFree(d_recs);
+static int ensure_json_staging(tbx_pool *p, int n) {
+  const size_t words = (size_t)n * p->info->rec_words;
+  if (p->j_cap_ids < (size_t)n) {
+    cudaFree(p->j_ids); p->j_ids = 0; p->j_cap_ids = 0;
+    const size_t cap = std::max<size_t>(1024, (size_t)n * 2);
+    CK(cudaMalloc(&p->j_ids, cap * sizeof(int32_t)));
+    p->j_cap_ids = cap;
+  }
+  if (p->j_cap_words < words) {
+    cudaFree(p->j_recs); cudaFreeHost(p->j_host); p->j_recs = p->j_host = 0; p->j_cap_words = 0;
+    const size_t cap = std::max<size_t>((size_t)1024 * p->info->rec_words, words * 2);
+    CK(cudaMalloc(&p->j_recs, cap * 4));
+    CK(cudaMallocHost(&p->j_host, cap * 4));
+    p->j_cap_words = cap;
+  }
   return TBX_OK;
 }
-static int store_records(tbx_pool *p, const int32_t *ids, int n, const std::vector<uint32_t> &recs) {
+/* records of the listed envs -> p->j_host (AoS).  Runs on the legacy default stream, which is ordered after the work of
+ * every blocking stream; callers on non-blocking streams synchronise first (the Python layer does). */
+static int fetch_records(tbx_pool *p, const int32_t *ids, int n) {
   const int rw = p->info->rec_words;
-  int32_t *d_ids = 0;
-  uint32_t *d_recs = 0;
-  CK(cudaMalloc(&d_ids, n * sizeof(int32_t)));
-  CK(cudaMalloc(&d_recs, recs.size() * 4));
-  CK(cudaMemcpy(d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_recs, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice));
-  scatter_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, d_ids, n, rw, d_recs);
+  for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= p->n) return set_err(TBX_EINVAL, "env id out of range");
+  CK(cudaSetDevice(p->device));
+  int r = ensure_json_staging(p, n);
+  if (r) return r;
+  if (p->hs) CK(cudaStreamSynchronize(p->hs));
+  CK(cudaMemcpyAsync(p->j_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+  gather_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, p->j_ids, n, rw, p->j_recs);
   CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  cudaFree(d_ids); cudaFree(d_recs);
+  CK(cudaMemcpyAsync(p->j_host, p->j_recs, (size_t)n * rw * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return TBX_OK;
+}
+/* p->j_host (AoS) -> the listed envs; the ids are still on the device from fetch_records */
+static int store_records(tbx_pool *p, int n) {
+  const int rw = p->info->rec_words;
+  CK(cudaMemcpyAsync(p->j_recs, p->j_host, (size_t)n * rw * 4, cudaMemcpyHostToDevice, 0));
+  scatter_kernel<<<blocks(n * rw, 256), 256>>>(p->planes, p->n_pad, p->j_ids, n, rw, p->j_recs);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(0));
   return TBX_OK;
 }
 
@@ -813,62 +844,75 @@ int tbx_state_to_json(tbx_pool *p, const int32_t *ids, int n, char **out) {
   if (!p || !ids || !out || n < 0) return set_err(TBX_EINVAL, "bad arguments");
   for (int i = 0; i < n; i++) out[i] = 0;
   if (n == 0) return TBX_OK;
-  std::vector<uint32_t> recs;
-  int r = fetch_records(p, ids, n, recs);
+  int r = fetch_records(p, ids, n);
   if (r) return r;
   const int rw = p->info->rec_words;
+  const uint32_t *recs = p->j_host;
   try {
-    for (int i = 0; i < n; i++) {
-      const uint32_t *R = recs.data() + (size_t)i * rw;
+    parallel_for(n, [&](int i) {
+      const uint32_t *R = recs + (size_t)i * rw;
       Value v;
       if (p->game == TBX_BREAKOUT) {
         const BrkRec &rec = *reinterpret_cast<const BrkRec *>(R);
-        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->brk_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
+        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->brk_tables.size()) throw std::runtime_error("corrupt table index");
         v = tbx::brk_state_to_json(rec, p->brk_tables[rec.hdr.tbl]);
       } else if (p->game == TBX_AMIDAR) {
         const AmiRec &rec = *reinterpret_cast<const AmiRec *>(R);
-        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->ami_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
+        if (rec.hdr.tbl < 0 || rec.hdr.tbl >= (int)p->ami_tables.size()) throw std::runtime_error("corrupt table index");
         v = tbx::ami_state_to_json(rec, p->ami_tables[rec.hdr.tbl]);
       } else v = tbx::si_state_to_json(*reinterpret_cast<const SiRec *>(R));
       out[i] = dup_str(tbxjson::dump(v));
-      if (!out[i]) return set_err(TBX_ENOMEM, "out of host memory");
-    }
-  } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+      if (!out[i]) throw std::runtime_error("out of host memory");
+    });
+  } catch (const std::exception &e) {
+    for (int i = 0; i < n; i++) { free(out[i]); out[i] = 0; }
+    return set_err(TBX_EJSON, e.what());
+  }
   return TBX_OK;
 }
 
 int tbx_state_from_json(tbx_pool *p, const int32_t *ids, int n, const char *const *json) {
   if (!p || !ids || !json || n < 0) return set_err(TBX_EINVAL, "bad arguments");
   if (n == 0) return TBX_OK;
-  std::vector<uint32_t> recs;
-  int r = fetch_records(p, ids, n, recs); /* keeps the fields JSON does not carry (simulator rand, episode counters) */
+  int r = fetch_records(p, ids, n); /* keeps the fields JSON does not carry (simulator rand, episode counters) */
   if (r) return r;
   const int rw = p->info->rec_words;
-  /* parse everything before touching the pool so a bad document leaves it unchanged */
-  std::vector<BrkTable> new_brk;
-  std::vector<AmiTable> new_ami;
+  uint32_t *recs = p->j_host;
+  /* parse everything (in parallel) before touching the pool so a bad document leaves it unchanged */
+  std::vector<BrkTable> new_brk(p->game == TBX_BREAKOUT ? n : 0);
+  std::vector<AmiTable> new_ami(p->game == TBX_AMIDAR ? n : 0);
   try {
-    for (int i = 0; i < n; i++) {
-      uint32_t *R = recs.data() + (size_t)i * rw;
+    parallel_for(n, [&](int i) {
+      uint32_t *R = recs + (size_t)i * rw;
       Value v = tbxjson::parse(json[i]);
-      if (p->game == TBX_BREAKOUT) { BrkTable t; tbx::brk_state_from_json(v, *reinterpret_cast<BrkRec *>(R), t); tbx::brk_mark_delta_ok(p->cfg, t); new_brk.push_back(t); }
-      else if (p->game == TBX_AMIDAR) { AmiTable t; tbx::ami_state_from_json(v, *reinterpret_cast<AmiRec *>(R), t); new_ami.push_back(t); }
+      if (p->game == TBX_BREAKOUT) { tbx::brk_state_from_json(v, *reinterpret_cast<BrkRec *>(R), new_brk[i]); tbx::brk_mark_delta_ok(p->cfg, new_brk[i]); }
+      else if (p->game == TBX_AMIDAR) tbx::ami_state_from_json(v, *reinterpret_cast<AmiRec *>(R), new_ami[i]);
       else tbx::si_state_from_json(v, *reinterpret_cast<SiRec *>(R));
-    }
+    });
   } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
   for (int i = 0; i < n; i++) {
-    uint32_t *R = recs.data() + (size_t)i * rw;
+    uint32_t *R = recs + (size_t)i * rw;
     if (p->game == TBX_BREAKOUT) reinterpret_cast<BrkRec *>(R)->hdr.tbl = intern(p->brk_tables, new_brk[i]);
     else if (p->game == TBX_AMIDAR) reinterpret_cast<AmiRec *>(R)->hdr.tbl = intern(p->ami_tables, new_ami[i]);
   }
   r = upload_tables(p);
   if (r) return r;
-  return store_records(p, ids, n, recs);
+  return store_records(p, n);
 }
 
+static uint64_t *cfg_rand(tbx::Config &c) { return c.game == TBX_BREAKOUT ? c.brk.rand : c.game == TBX_AMIDAR ? c.ami.rand : c.si.rand; }
 int tbx_config_to_json(tbx_pool *p, char **out) {
   if (!p || !out) return set_err(TBX_EINVAL, "bad arguments");
-  try { *out = dup_str(tbxjson::dump(tbx::config_to_json(p->cfg))); } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
+  /* ctoybox's config_to_json shows the simulator as it is NOW: `rand` is the simulator rng that new_game has advanced.
+   * A pool keeps one simulator rng per env; the pool-level document reports env 0's (the batch-1 shim's only env). */
+  tbx::Config c = p->cfg;
+  CK(cudaSetDevice(p->device));
+  uint32_t w[4];
+  CK(cudaMemcpy2D(w, sizeof(uint32_t), p->planes + (size_t)TBX_HW(sim_rand) * p->n_pad, (size_t)p->n_pad * sizeof(uint32_t), sizeof(uint32_t), 4,
+                  cudaMemcpyDeviceToHost));
+  cfg_rand(c)[0] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+  cfg_rand(c)[1] = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+  try { *out = dup_str(tbxjson::dump(tbx::config_to_json(c))); } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
   return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");
 }
 int tbx_config_from_json(tbx_pool *p, const char *json) {
@@ -882,6 +926,9 @@ int tbx_config_from_json(tbx_pool *p, const char *json) {
   install_default_table(p);
   int r = upload_tables(p);
   if (r) return r;
+  /* write_config_json replaces the simulator, its rng included: every env's simulator rng restarts from the document's */
+  set_sim_rand_kernel<<<blocks(p->n, 256), 256>>>(p->planes, p->n, p->n_pad, cfg_rand(p->cfg)[0], cfg_rand(p->cfg)[1]);
+  CK(cudaGetLastError());
   return upload_cfg(p);
 }
 int tbx_schema_for_state(const char *game, char **out) {
@@ -903,17 +950,18 @@ int tbx_query_json(tbx_pool *p, int env, const char *query, const char *args_jso
   try {
     Value args = tbxjson::parse(args_json ? args_json : "null");
     std::string q(query);
-    std::vector<uint32_t> recs;
+    const uint32_t *rec = 0;
     const BrkTable *brk = 0;
     if (p->game == TBX_BREAKOUT) {
       int32_t id = env;
-      int r = fetch_records(p, &id, 1, recs);
+      int r = fetch_records(p, &id, 1);
       if (r) return r;
-      int tbl = reinterpret_cast<const BrkRec *>(recs.data())->hdr.tbl;
+      rec = p->j_host;
+      int tbl = reinterpret_cast<const BrkRec *>(rec)->hdr.tbl;
       if (tbl < 0 || tbl >= (int)p->brk_tables.size()) return set_err(TBX_EINVAL, "corrupt table index");
       brk = &p->brk_tables[tbl];
     }
-    Value res = tbx::query_json(p->game, recs.data(), brk, q, args);
+    Value res = tbx::query_json(p->game, rec, brk, q, args);
     *out = dup_str(tbxjson::dump(res));
   } catch (const std::exception &e) { return set_err(TBX_EJSON, e.what()); }
   return *out ? TBX_OK : set_err(TBX_ENOMEM, "out of host memory");

@@ -18,50 +18,79 @@
 #define TBX_RENDER_DIRECT_CUH
 #include "tbx_render_area.cuh"
 #include "tbx_direct.h"
+#include "tbx_direct_launch.h"
 
 namespace tbxk {
 
-struct DirectArgs {
-  const void *aux;    /* the game's closed-form tables on the device (TbxBrkDirect ...) */
-  int32_t *fb_list;   /* envs handed to the tile kernel */
-  int *fb_count;
-  int hstride;        /* floats per H row in shared memory */
-  int warp_bytes;     /* shared memory per warp */
-};
-
 #define TBX_DIRECT_THREADS 256
+#ifndef TBX_DIRECT_MIN_CTAS
+#define TBX_DIRECT_MIN_CTAS 4
+#endif
 
+/* 16-byte asynchronous copies global -> shared (LDGSTS): the next chunk's records travel while this one is rendered */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* PERSISTENT CTAs: CTA b renders the chunks (8 consecutive envs, one per warp) b, b + gridDim.x, ...  Shared memory:
+ * the down-sample of base frame 1 (loaded once per CTA; every env's frame starts as ONE bulk shared -> global copy of it,
+ * cp.async.bulk, no per-env load/store instructions), two stages of word-major records (cp.async prefetch of the next
+ * chunk), and per warp its env's record, the wall's H rows and the movers' records. */
 template <int TX, int TY>
-__global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ BrkCfg cfg_c,
+__global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ BrkCfg cfg_c,
                                                                             const __grid_constant__ TbxAreaPlan plan_c, const __grid_constant__ DirectArgs d) {
   constexpr int RW = TBX_WORDS(BrkRec);
+  constexpr int RECW_BYTES = (RW * 4 + 15) & ~15;
   extern __shared__ uint4 smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
-  uint32_t *recs = reinterpret_cast<uint32_t *>(smem);
+  uint8_t *sbase = smem;                                                        /* base frame 1, down-sampled */
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2][RW][8 envs] */
   const TbxBrkDirect *__restrict__ Ap = reinterpret_cast<const TbxBrkDirect *>(d.aux);
   const TbxBrkDirect &A = *Ap;
   const TbxAreaPlan *__restrict__ plan = a.plan; /* per-lane indexed reads */
   const TbxAreaPlan &cp = plan_c;                /* warp-uniform reads: constant bank */
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
-  const int e0 = blockIdx.x * TBX_EPC;
-  const int ne = min(TBX_EPC, a.n - e0);
-  for (int i = tid; i < RW * TBX_EPC; i += blockDim.x) {
-    const int w = i / TBX_EPC, j = i - w * TBX_EPC;
-    if (j < ne) recs[j * RW + w] = a.planes[(size_t)w * a.n_pad + e0 + j];
-  }
-  __syncthreads(); /* the only CTA barrier */
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint8_t *wmem = smem + d.smem_base + 2 * RW * TBX_EPC * 4 + wid * d.warp_bytes;
+  uint32_t *recw = reinterpret_cast<uint32_t *>(wmem);                          /* this warp's env, as a record */
+  float *hw = reinterpret_cast<float *>(wmem + RECW_BYTES);
+  int4 *mrec = reinterpret_cast<int4 *>(wmem + d.warp_bytes - 256);             /* 3 x int4 per mover */
+  const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
+  const int dw = cp.dw, dh = cp.dh, nwords = dw >> 2, hs = d.hstride, nb = dw * dh;
+  const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
+
+  auto prefetch = [&](int chunk, int st) { /* 2 x 16 bytes per state word: the 8 envs of the chunk */
+    const uint32_t *src = a.planes + (size_t)chunk * TBX_EPC;
+    uint32_t *dst = stage + st * RW * TBX_EPC;
+    for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(dst + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
+  for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk copies below read sbase through the async proxy */
 
   const int ok = A.ok, ncols = A.ncols, nrows = A.nrows, wdy0 = A.wdy0, wdy1 = A.wdy1, hud_dyhi = A.hud_dyhi;
   const int wy0 = A.wy0, wy1 = A.wy0 + A.nrows * A.bh;
-  const int dw = cp.dw, dh = cp.dh, nwords = dw >> 2, hs = d.hstride;
-  float *hw = reinterpret_cast<float *>(smem + a.smem_canvas + wid * d.warp_bytes);
+  const uint32_t paddle_gray = A.paddle_gray, ball_gray = A.ball_gray;
   const TbxDigitPatch *__restrict__ patches = a.patches[1];
+  const uint32_t *R = recw;
 
-  for (int j = wid; j < ne; j += nwarps) {
-    const uint32_t *R = recs + j * RW;
-    const int env = e0 + j;
+  int st = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, st ^= 1) {
+    cp_async_wait_all();
+    __syncthreads(); /* this chunk's records have landed; every warp is done with the other stage */
+    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x, st ^ 1);
+    const int env = chunk * TBX_EPC + wid;
+    if (env >= a.n) continue;
+    {
+      const uint32_t *src = stage + st * RW * TBX_EPC + wid;
+      for (int w = lane; w < RW; w += 32) recw[w] = src[w * TBX_EPC];
+    }
+    __syncwarp();
+    uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
     /* movers: lane 0 the paddle, lanes 1..4 the balls; footprint = the output pixels the rectangle feeds */
-    const TbxMover mine = brk_mover(R, cfg_c, A, lane < BRK_N_MOVERS ? lane : -1);
+    const TbxMover mine = brk_mover(R, cfg_c, paddle_gray, ball_gray, lane < BRK_N_MOVERS ? lane : -1);
     const bool valid = mine.x0 < mine.x1;
     int fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;
     if (valid) { fx0 = __ldg(&plan->xdlo[mine.x0]); fx1 = __ldg(&plan->xdhi[mine.x1 - 1]); fy0 = __ldg(&plan->ydlo[mine.y0]); fy1 = __ldg(&plan->ydhi[mine.y1 - 1]); }
@@ -79,19 +108,128 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const
       if (lane == 0) d.fb_list[atomicAdd(d.fb_count, 1)] = env;
       continue;
     }
-    uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
-    { /* 1. every brick alive, nothing else */
-      const uint4 *src = reinterpret_cast<const uint4 *>(a.base_out[1]);
-      const int nb = dw * dh;
-#pragma unroll 4
-      for (int i = lane; i < (nb >> 4); i += 32) reinterpret_cast<uint4 *>(out)[i] = __ldg(src + i);
-      for (int i = ((nb >> 4) << 2) + lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t *>(out)[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+    /* 1. every brick alive, nothing else: one bulk copy of the staged base frame, in flight while the warp prepares 2..4 */
+    if (bulk) {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"((uint32_t)__cvta_generic_to_shared(sbase)), "r"((uint32_t)nb) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int i = lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(sbase)[i];
     }
+    /* 4a. paddle and balls, prepared while the base copy is in flight.  Lane m < 5 publishes its mover (rectangle, gray,
+     * footprint) in the warp's shared memory; the footprints' output pixels form one list that the lanes share out 32 at
+     * a time, whichever mover they belong to.  A pixel's TX x TY source window is built as packed bytes -- base frame 0
+     * (two aligned word loads and a funnel shift per row), the brick grid where the window meets the wall, then every
+     * mover's rectangle in draw order as a byte mask -- and resolved in cv2's tap order.  The first 32 pixels are computed
+     * here and written in 4b, after the wall's and the HUD's. */
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid) & ((1u << BRK_N_MOVERS) - 1u);
+    if (lane < BRK_N_MOVERS) {
+      const int ncol = valid ? fx1 - fx0 + 1 : 0, nrow = valid ? fy1 - fy0 + 1 : 0;
+      mrec[3 * lane + 0] = make_int4(mine.x0, mine.y0, mine.x1, mine.y1);
+      mrec[3 * lane + 1] = make_int4((int)mine.gray * 0x01010101, fx0, fy0, ncol);
+      mrec[3 * lane + 2] = make_int4(ncol * nrow, ncol > 1 ? (int)__ldg(&A.inv32[ncol]) : 0, 0, 0);
+    }
+    __syncwarp();
+    int total = 0;
+#pragma unroll
+    for (int m = 0; m < BRK_N_MOVERS; m++) total += mrec[3 * m + 2].x;
+    const uint32_t *__restrict__ base0w = reinterpret_cast<const uint32_t *>(a.base[0]);
+    const uint32_t *alive = R + BRK_W(alive);
+    /* pixel p0 + lane of the movers' list: its offset in the frame (-1: past the end) and its value */
+    auto mover_pixel = [&](int p0, int &o) -> uint32_t {
+      const int l = p0 + lane;
+      int mym = 0, myi = 0, off = 0;
+#pragma unroll
+      for (int m = 0; m < BRK_N_MOVERS; m++) {
+        const int cnt = mrec[3 * m + 2].x;
+        if (l >= off && l < off + cnt) { mym = m; myi = l - off; }
+        off += cnt;
+      }
+      const bool act = l < total;
+      const int4 f = mrec[3 * mym + 1];
+      const int ncol = f.w, inv = mrec[3 * mym + 2].y;
+      const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, (unsigned)inv) : myi;
+      const int dx = act ? f.y + myi - q * ncol : 0, dy = act ? f.z + q : 0;
+      o = act ? dy * dw + dx : -1;
+      const int xs = __ldg(&plan->xs0[dx]), ys = __ldg(&plan->ys0[dy]);
+      /* source rows as packed bytes: lo = taps 0..3, hi = tap 4 (TX == 5) */
+      uint32_t lo[TY], hi[TY];
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        const int y = min(ys + k, TBX_BRK_H - 1); /* surplus taps carry zero weights: any in-frame pixel will do */
+        const int ob = y * TBX_BRK_W + xs;
+        const uint32_t w0 = __ldg(base0w + (ob >> 2)), w1 = __ldg(base0w + (ob >> 2) + 1); /* the frame buffer has 16 bytes of slack */
+        lo[k] = __funnelshift_r(w0, w1, 8 * (ob & 3));
+        hi[k] = 0;
+        if (TX > 4) { const uint32_t w2 = __ldg(base0w + (ob >> 2) + 2); hi[k] = __funnelshift_r(w1, w2, 8 * (ob & 3)) & 255u; }
+      }
+      if (__any_sync(0xffffffffu, act && ys < wy1 && ys + TY > wy0)) { /* the brick grid */
+        uint32_t cb[TX];
+#pragma unroll
+        for (int t = 0; t < TX; t++) cb[t] = __ldg(&A.xcol[min(xs + t, TBX_BRK_W - 1)]);
+#pragma unroll
+        for (int k = 0; k < TY; k++) {
+          const uint32_t r = __ldg(&A.yrow[min(ys + k, TBX_BRK_H - 1)]);
+          if (r == 255u) continue;
+#pragma unroll
+          for (int t = 0; t < TX; t++) {
+            if (cb[t] == 255u) continue;
+            const uint32_t i = cb[t] * (uint32_t)nrows + r;
+            if (!((alive[i >> 5] >> (i & 31)) & 1u)) continue;
+            const uint32_t g = __ldg(&A.brickgray[i]);
+            if (t < 4) lo[k] = (lo[k] & ~(255u << (8 * t))) | (g << (8 * t));
+            else hi[k] = g;
+          }
+        }
+      }
+      uint32_t mleft = vm;
+      while (mleft) { /* draw order: paddle, then the balls */
+        const int m = __ffs(mleft) - 1;
+        mleft &= mleft - 1;
+        const int4 rc = mrec[3 * m];
+        const uint32_t g4 = (uint32_t)mrec[3 * m + 1].x;
+        const int ta = max(rc.x - xs, 0), tb = min(rc.z - xs, TX), ka = max(rc.y - ys, 0), kb = min(rc.w - ys, TY);
+        if (ta >= tb || ka >= kb) continue;
+        const uint32_t below_b = tb >= 4 ? 0xffffffffu : (1u << (8 * tb)) - 1u, below_a = ta >= 4 ? 0xffffffffu : (1u << (8 * ta)) - 1u;
+        const uint32_t bm = below_b & ~below_a;
+        const bool h5 = TX > 4 && ta <= 4 && tb > 4;
+#pragma unroll
+        for (int k = 0; k < TY; k++)
+          if (k >= ka && k < kb) {
+            lo[k] = (lo[k] & ~bm) | (g4 & bm);
+            if (h5) hi[k] = g4 & 255u;
+          }
+      }
+      float al[TX];
+#pragma unroll
+      for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        float h = tbx_fmul(tbx_u8f(lo[k] & 255u), al[0]);
+#pragma unroll
+        for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(t < 4 ? (lo[k] >> (8 * t)) & 255u : hi[k]), al[t]));
+        const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+        acc = k == 0 ? bh : tbx_fadd(acc, bh);
+      }
+      const int iv = tbx_f2i_rn_small(acc);
+      return (uint32_t)(iv > 255 ? 255 : iv); /* a sum of non-negative terms: never below zero */
+    };
+    int o_first = -1;
+    uint32_t v_first = 0;
+    if (total > 0) v_first = mover_pixel(0, o_first);
     /* 2. the wall */
     const uint32_t fullm = (1u << nrows) - 1u;
     const uint32_t colbits = lane < ncols ? brk_col_bits(R + BRK_W(alive), nrows, lane) : fullm;
     const uint32_t deadcols = __ballot_sync(0xffffffffu, colbits != fullm);
-    __syncwarp(); /* orders the base copy before the patches other lanes write below */
+    bool landed = false; /* the base copy must have landed before the first patch is written over it */
+#define TBX_DIRECT_LAND()                                                                       \
+    if (!landed) {                                                                              \
+      if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          \
+      __syncwarp();                                                                             \
+      landed = true;                                                                            \
+    }
     if (deadcols) {
       const uint32_t deadrows = __reduce_or_sync(0xffffffffu, ~colbits & fullm);
       uint32_t rowmask[TBX_BRK_MAX_ROWS];
@@ -101,6 +239,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const
       const uint32_t rmask = __ballot_sync(0xffffffffu, wdy0 + lane <= wdy1 && (__ldg(&A.dyrows[wdy0 + lane]) & deadrows));
       if (wmask && rmask) {
         const int wlo = __ffs(wmask) - 1, whi = 31 - __clz(wmask);
+        __syncwarp(); /* the previous env's readers of the H rows are done */
         for (int dx = 4 * wlo + lane; dx < 4 * whi + 4; dx += 32) {
           const int c0 = __ldg(&A.col0[dx]);
 #pragma unroll
@@ -108,6 +247,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const
             if (r < nrows) hw[r * hs + dx] = __ldg(&A.hlut[r][(rowmask[r] >> c0) & 3u][dx]);
         }
         __syncwarp();
+        TBX_DIRECT_LAND();
         const int naw = __popc(wmask), rlo = wdy0 + __ffs(rmask) - 1, rhi = wdy0 + 31 - __clz(rmask);
         const int lg = naw > 16 ? 5 : naw > 8 ? 4 : naw > 4 ? 3 : naw > 2 ? 2 : naw > 1 ? 1 : 0;
         const int jw = lane & ((1 << lg) - 1), sub = lane >> lg, rpi = 32 >> lg;
@@ -130,13 +270,14 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const int iv = tbx_f2i_rn_small(acc[q]);
-            word |= (uint32_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv) << (8 * q);
+            word |= (uint32_t)(iv > 255 ? 255 : iv) << (8 * q); /* a sum of non-negative terms: never below zero */
           }
           *reinterpret_cast<uint32_t *>(out + dy * dw + 4 * myword) = word;
         }
       }
     }
     /* 3. HUD digits: one patch at a time, lanes over (row, column) */
+    TBX_DIRECT_LAND();
     {
       uint32_t dm = __ballot_sync(0xffffffffu, dig >= 0);
       while (dm) {
@@ -150,42 +291,15 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, 4) brk_direct_kernel(const
       }
     }
     __syncwarp(); /* the movers' pixels go over the wall's */
-    /* 4. paddle and balls */
-    uint32_t mm = __ballot_sync(0xffffffffu, valid) & ((1u << BRK_N_MOVERS) - 1u);
-    if (mm) {
-      TbxMover mv[BRK_N_MOVERS];
-#pragma unroll
-      for (int m = 0; m < BRK_N_MOVERS; m++) {
-        mv[m].x0 = __shfl_sync(0xffffffffu, mine.x0, m); mv[m].x1 = __shfl_sync(0xffffffffu, mine.x1, m);
-        mv[m].y0 = __shfl_sync(0xffffffffu, mine.y0, m); mv[m].y1 = __shfl_sync(0xffffffffu, mine.y1, m);
-        mv[m].gray = __shfl_sync(0xffffffffu, mine.gray, m);
-      }
-      const uint8_t *__restrict__ base0 = a.base[0];
-      const uint32_t vm = mm;
-      while (mm) {
-        const int m = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const int dx0 = __shfl_sync(0xffffffffu, fx0, m), dx1 = __shfl_sync(0xffffffffu, fx1, m);
-        const int dy0 = __shfl_sync(0xffffffffu, fy0, m), dy1 = __shfl_sync(0xffffffffu, fy1, m);
-        /* the movers that reach into the source window of this footprint, and whether the wall does */
-        const int sx0 = cp.xs0[dx0], sx1 = cp.xs0[dx1] + TX, sy0 = cp.ys0[dy0], sy1 = cp.ys0[dy1] + TY;
-        uint32_t near = 0;
-#pragma unroll
-        for (int q = 0; q < BRK_N_MOVERS; q++)
-          if (((vm >> q) & 1u) && mv[q].x0 < sx1 && mv[q].x1 > sx0 && mv[q].y0 < sy1 && mv[q].y1 > sy0) near |= 1u << q;
-        const bool wall = sy0 < wy1 && sy1 > wy0;
-        const int ncol = dx1 - dx0 + 1;
-        const int lg = ncol > 16 ? 5 : ncol > 8 ? 4 : ncol > 4 ? 3 : ncol > 2 ? 2 : ncol > 1 ? 1 : 0;
-        const int c = lane & ((1 << lg) - 1), cpl = 1 << lg, rstep = 32 >> lg;
-        for (int dxb = dx0; dxb <= dx1; dxb += cpl) {
-          const int dx = dxb + c;
-          if (dx > dx1) continue;
-          for (int dy = dy0 + (lane >> lg); dy <= dy1; dy += rstep)
-            out[dy * dw + dx] = brk_direct_pixel<TX, TY>(A, *plan, base0, R + BRK_W(alive), mv, near, wall, dx, dy);
-        }
-      }
+    /* 4b. the movers' pixels */
+    if (o_first >= 0) out[o_first] = (uint8_t)v_first;
+    for (int p0 = 32; p0 < total; p0 += 32) {
+      int o;
+      const uint32_t v = mover_pixel(p0, o);
+      if (o >= 0) out[o] = (uint8_t)v;
     }
   }
+#undef TBX_DIRECT_LAND
 }
 
 } /* namespace tbxk */

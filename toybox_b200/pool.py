@@ -236,6 +236,14 @@ class BatchedToybox:
         _lib.check(self.L.tbx_stats_read(self._h, out, int(reset), _stream(self.device)))
         return [int(v) for v in out]
 
+    def episode_stats_into(self, out):
+        """The same four counters copied into `out` (int64[4] on the pool's device) in stream order, without a host
+        synchronisation -- the form a collective inside a timed region consumes."""
+        if out.dtype != torch.int64 or out.numel() != 4 or out.device != self.device:
+            raise ValueError("out must be int64[4] on the pool's device")
+        _lib.check(self.L.tbx_stats_read_device(self._h, _ptr(out), _stream(self.device)))
+        return out
+
     # ------------------------------------------------------------------ vectorised properties (no JSON round trip)
     def property_info(self, path):
         """(word, kind, bit) of a scalar of the state schema; kind: 0 int32, 1 float64, 2 bool, 3 bit, 4 Option<i32>."""
