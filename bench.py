@@ -220,10 +220,114 @@ def wrapped_arm(args):
     env.close()
 
 
+def interventions_arm(args):
+    """Supplementary measurement, BASELINE.json configs[3]: Space Invaders, 262,144 envs (--envs), gray84, random actions; every
+    64 steps the state JSON of 1,024 random envs is exported, mutated (lives, ufo.appearance_counter, one shield pixel) and
+    imported again -- the batched form of toybox/interventions/base.py:387-408.  Reports env-steps/s with and without the
+    interventions, and the JSON throughput of both directions, for the dict-level API (what the reference's Intervention does)
+    and for the text-level API (export text, edit only what changes)."""
+    import numpy as np
+    import torch
+    import toybox_b200
+    toybox_b200.lib()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    game = args.game if args.game != "breakout" else "space_invaders"
+    n = args.envs if args.envs != 65536 else 262144
+    pool = toybox_b200.BatchedToybox(game, n, device=dev, obs=args.obs, seeds=(1234 + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF)
+    obs = torch.empty((n,) + pool.obs_shape, dtype=torch.uint8, device=dev)
+    acts = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    rng = np.random.default_rng(7)
+    t = [0]
+
+    def step(render=True):
+        pool.fill_random_actions(acts, ACTION_SEED, t[0], 0)
+        pool.apply_ale_action(acts, auto_reset=True)
+        if render:
+            pool.render(out=obs)
+        t[0] += 1
+
+    def mutate(js):
+        js["lives"] = 1 + int(rng.integers(5))
+        if "ufo" in js:
+            js["ufo"]["appearance_counter"] = int(rng.integers(1, 400))
+            sh = js["shields"][int(rng.integers(3))]
+            px = sh["data"][int(rng.integers(len(sh["data"])))]
+            px[int(rng.integers(len(px)))] = {"r": 0, "g": 0, "b": 0, "a": 0}
+        return js
+
+    jstat = {"export_s": 0.0, "import_s": 0.0, "bytes": 0, "rounds": 0, "host_edit_s": 0.0}
+
+    def intervene(text_level):
+        ids = rng.choice(n, size=1024, replace=False).astype(np.int32)
+        torch.cuda.synchronize(dev)          # the queued steps finish first: the export timer sees the codec, not the rollout
+        t0 = time.perf_counter()
+        docs = pool.to_state_json_text(ids)
+        t1 = time.perf_counter()
+        if text_level:      # decode / re-encode only every 8th document; the others go back as the text they came as
+            docs = [json.dumps(mutate(json.loads(d))).encode() if i % 8 == 0 else d for i, d in enumerate(docs)]
+        else:
+            docs = [mutate(json.loads(d)) for d in docs]
+        t2 = time.perf_counter()
+        pool.write_state_json(docs, ids)
+        t3 = time.perf_counter()
+        jstat["export_s"] += t1 - t0
+        jstat["host_edit_s"] += t2 - t1
+        jstat["import_s"] += t3 - t2
+        jstat["bytes"] += sum(len(d) if isinstance(d, bytes) else 0 for d in docs) if text_level else 0
+        jstat["rounds"] += 1
+        return sum(len(d) for d in docs) if text_level else None
+
+    for _ in range(args.presteps):
+        step(render=False)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    intervene(True)
+    torch.cuda.synchronize(dev)
+    K = max(args.steps, 128)
+
+    def run(mode):
+        for k in jstat:
+            jstat[k] = 0
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(K):
+            step()
+            if mode is not None and k % 64 == 63:
+                intervene(mode == "text")
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, dict(jstat)
+
+    sec_plain, _ = run(None)
+    sec_dict, st_dict = run("dict")
+    sec_text, st_text = run("text")
+    doc_bytes = len(pool.to_state_json_text([0])[0])
+
+    def jrec(sec, st):
+        mb = 1024 * doc_bytes * st["rounds"] / 1e6
+        return {"value": n * K / sec, "unit": "env-steps/s", "rounds": st["rounds"], "export_MBps": mb / st["export_s"] if st["export_s"] else None,
+                "import_MBps": mb / st["import_s"] if st["import_s"] else None, "export_ms_per_round": 1e3 * st["export_s"] / max(st["rounds"], 1),
+                "import_ms_per_round": 1e3 * st["import_s"] / max(st["rounds"], 1), "host_edit_ms_per_round": 1e3 * st["host_edit_s"] / max(st["rounds"], 1)}
+
+    line = {"metric": "env-steps/sec with rendered frames and mid-rollout JSON state interventions", "value": n * K / sec_dict, "unit": "env-steps/s",
+            "n_gpus": 1, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * sec_dict / K, "higher_is_better": True, "supplementary": True,
+            "dtype": GAME_DTYPE[game], "data": "synthetic", "timing": "host wall clock around K steps incl. the interventions (they synchronise)",
+            "config": {"workload": "%s %d envs, %s obs, random legal actions, auto-reset; every 64 steps: to_state_json of 1,024 random envs, mutate lives / "
+                                   "ufo.appearance_counter / one shield pixel, write_state_json" % (game, n, args.obs),
+                       "presteps": args.presteps, "json_bytes_per_env": doc_bytes},
+            "without_interventions": {"value": n * K / sec_plain, "unit": "env-steps/s"},
+            "dict_level_api": jrec(sec_dict, st_dict), "text_level_api": jrec(sec_text, st_text),
+            "gpu_launches": 3 * K, "episode_stats": pool.episode_stats()}
+    print(json.dumps(line), flush=True)
+    pool.close()
+
+
 def mixed_arm(args):
     """Supplementary measurement, BASELINE.json configs[4]: the mixed-game sweep.  Every rank owns one pool per game
     (its shard of that game's env-id range, seeds from the global env id); a step = fill + step + render of all three
-    pools; every 256 steps the per-game episode statistics are all-reduced (NCCL) -- the path's only collective."""
+    pools; every 256 steps the per-game episode statistics are all-reduced (NCCL, device side, inside the timed region) --
+    the path's only collective."""
     import numpy as np
     import torch
     import toybox_b200
@@ -247,28 +351,44 @@ def mixed_arm(args):
         pools.append((pool, env0, n))
         bufs.append((torch.empty((n,) + pool.obs_shape, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev)))
     stream = torch.cuda.current_stream(dev)
-    reduced = [None] * 3
+    sdev = torch.zeros((3, 4), dtype=torch.int64, device=dev)
+    n_reduces = [0]
 
-    def step(t):
+    def reduce_all():
+        for k, (pool, _, _) in enumerate(pools):
+            pool.episode_stats_into(sdev[k])
+        if dist is not None:
+            mx = sdev[:, 3].clone()
+            dist.all_reduce(sdev, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sdev[:, 3] = mx
+        n_reduces[0] += 1
+
+    def step(t, render=True):
         for (pool, env0, n), (obs, acts) in zip(pools, bufs):
             pool.fill_random_actions(acts, ACTION_SEED, t, env0)
             pool.apply_ale_action(acts, auto_reset=True)
-            pool.render(out=obs)
-        if t % 256 == 255:
-            for k, (pool, _, _) in enumerate(pools):
-                reduced[k] = D.reduce_episode_stats(pool.episode_stats(), device=dev)
+            if render:
+                pool.render(out=obs)
+        if render and t % 256 == 255:
+            reduce_all()
 
     t = 0
+    for _ in range(args.presteps):          # steady state: episodes end and restart inside the run
+        step(t, render=False)
+        t += 1
     for _ in range(max(args.warmup, 3)):
         step(t)
         t += 1
+    reduce_all()
+    n_reduces[0] = 0
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    K = args.steps
+    K = max(args.steps, 512)                # at least two statistics reduces inside the timed region
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -280,7 +400,9 @@ def mixed_arm(args):
     ms = e0.elapsed_time(e1)
     for pool, _, _ in pools:
         pool.check()
-    stats = [D.reduce_episode_stats(pool.episode_stats(), device=dev) for pool, _, _ in pools]
+    reduces_in_region = n_reduces[0]
+    reduce_all()
+    stats = [[int(v) for v in row] for row in sdev.cpu()]
     if dist is not None:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -291,8 +413,10 @@ def mixed_arm(args):
                 "scaling": "strong", "supplementary": True, "dtype": "f64+i32+u8", "data": "synthetic",
                 "config": {"workload": "mixed-game sweep: %d envs total = %s, split evenly over %d GPU(s), gray84 obs, random legal actions, "
                                        "auto-reset, NCCL all-reduce of per-game episode statistics every 256 steps"
-                                       % (args.mixed, " + ".join("%d %s" % (n, g) for g, n in zip(games, per_game)), world)},
-                "gpu_launches": 9 * K, "collective": "all_reduce of 3 x [episodes, sum_return, sum_length, max_return] int64 every 256 steps",
+                                       % (args.mixed, " + ".join("%d %s" % (n, g) for g, n in zip(games, per_game)), world),
+                           "presteps": args.presteps},
+                "gpu_launches": 9 * K, "collective": {"op": "all_reduce (SUM + MAX) of 3 x [episodes, sum_return, sum_length | max_return] int64",
+                                                      "every_steps": 256, "inside_timed_region": reduces_in_region},
                 "episode_stats": {g: s for g, s in zip(games, stats)}}
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -369,10 +493,13 @@ def main():
                 self.pool.fill_random_actions(self.actions, ACTION_SEED, self.t, self.env0)
 
         def step(self, ev=None, render=True):
-            self.fill()
             if ev is not None:
                 ev[0].record(stream)
-            self.pool.apply_ale_action(self.actions, auto_reset=True)
+            if self.policy == "track":
+                self.fill()
+                self.pool.apply_ale_action(self.actions, auto_reset=True)
+            else:       # the uniform stream is generated inside the step kernel (tbx_step_random): one launch
+                self.pool.step_random(ACTION_SEED, self.t, self.env0, auto_reset=True)
             if ev is not None:
                 ev[1].record(stream)
             if render:
@@ -607,7 +734,7 @@ def main():
         v, s = cpu_rollout(args.game, args.obs, n_cpu, steps_cpu, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": "%d envs x %d frames (step + %s render), %.1f s, oracle/ C restatement with OpenMP" % (n_cpu, steps_cpu, args.obs, s)}
-    launches = ["fill_actions_kernel", "step_kernel", kname] + (["area_tile_kernel (env-list mode, normally empty)"] if kname == "brk_direct_kernel" else [])
+    launches = (["step_kernel (synthetic action stream fused)"] if args.policy == "random" else ["breakout_tracking_actions_kernel", "step_kernel"]) + [kname] + (["area_tile_kernel (env-list mode, normally empty)"] if kname == "brk_direct_kernel" else [])
     line = {
         "metric": "env-steps/sec with rendered frames", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -79,6 +79,10 @@ int tbx_step(tbx_pool *pool, const int32_t *actions_dev, int auto_reset, int32_t
  * inputs_dev: uint8[N] bitmask left=1 right=2 up=4 down=8 button1=16 button2=32. */
 int tbx_step_inputs(tbx_pool *pool, const uint8_t *inputs_dev, int auto_reset, int32_t *reward_dev, uint8_t *done_dev,
                     int32_t *score_dev, int32_t *lives_dev, void *stream);
+/* The same step driven by the benchmark's synthetic action stream (tbx_fill_actions below), generated inside the step kernel:
+ * env i takes legal[index(seed, env0 + i, t)].  One launch instead of two; bit-identical to tbx_fill_actions + tbx_step. */
+int tbx_step_random(tbx_pool *pool, uint64_t seed, uint64_t env0, uint64_t t, int auto_reset, int32_t *reward_dev, uint8_t *done_dev,
+                    int32_t *score_dev, int32_t *lives_dev, void *stream);
 /* synchronises `stream` and returns TBX_EACTION if any env received an invalid action id since the last check */
 int tbx_check(tbx_pool *pool, void *stream);
 
@@ -111,6 +115,12 @@ int tbx_schema_for_config(const char *game, char **out_json);
 /* state_query_json: Toybox.query_state_json(query, args) (interventions/amidar.py:508-518) for one env */
 int tbx_query_json(tbx_pool *pool, int env_id, const char *query, const char *args_json, char **out_json);
 void tbx_free_str(char *s);
+
+/* BreakoutIntervention.add_channel(col) / fill_column(col) (toybox/interventions/breakout.py:406-416) and the channel count
+ * behind rstate.breakout_channel_count() (baselines/baselines/run_get_seed_state.py:266-270) for every env in one launch:
+ * op 0 = the bricks of column `col` dead, 1 = alive again (mask_dev, uint8[N] or NULL, selects the envs), 2 = out_dev[env] =
+ * columns with no alive brick (int32[N]).  Columns follow each env's own brick table (bricks[i].col). */
+int tbx_breakout_columns(tbx_pool *pool, int op, int col, const uint8_t *mask_dev, int32_t *out_dev, void *stream);
 
 /* Episode statistics accumulated on the device since the last reset of the counters (the role of
  * baselines/baselines/bench/monitor.py:58-76): out_host[0..3] = episodes finished, sum of episode returns,
@@ -157,6 +167,14 @@ int tbx_field_set(tbx_pool *pool, const char *path, const void *values_dev, cons
 typedef struct tbx_wrap tbx_wrap;
 int tbx_wrap_create(tbx_pool *pool, int skip, int noop_max, int episodic_life, int fire_reset, int clip_rewards, int stack_k,
                     int out_w, int out_h, uint64_t noop_seed, uint64_t env0, tbx_wrap **out);
+/* What a reset observation does to the other k-1 slots of an env's ring: 0 (default) = it fills them, FrameStack.reset
+ * (baselines/baselines/common/atari_wrappers.py:262-266, the wrap_deepmind(frame_stack=True) path); 1 = they are zeroed,
+ * VecFrameStack (baselines/baselines/common/vec_env/vec_frame_stack.py:17-30, the make_vec_env + VecFrameStack path). */
+int tbx_wrap_set_stack_mode(tbx_wrap *w, int mode);
+/* Device buffers (int32[N] each, caller-owned, may be NULL) that every tbx_wrap_step fills with baselines' Monitor record
+ * (bench/monitor.py:58-76; Monitor sits between make_atari and wrap_deepmind, common/cmd_util.py:30-36) of the episode that
+ * ended in that agent step: r = sum of raw rewards, l = MaxAndSkipEnv steps since the last real reset.  Valid where real_done. */
+int tbx_wrap_set_episode_outputs(tbx_wrap *w, int32_t *ep_return_dev, int32_t *ep_length_dev);
 int tbx_wrap_destroy(tbx_wrap *wrap);
 /* env.step(action) of the wrapped env for every env (actions_dev: int32[N] gym action indices into the legal set), or
  * env.reset() for every env when actions_dev == NULL.  obs_ring_dev: uint8[N][stack_k][out_h][out_w], a ring of the

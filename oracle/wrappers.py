@@ -89,6 +89,28 @@ class MaxAndSkipEnv:                                    # atari_wrappers.py:186-
         return self.env.reset()
 
 
+class Monitor:                                          # baselines/baselines/bench/monitor.py:36-76 (between make_atari and wrap_deepmind,
+    def __init__(self, env):                            # common/cmd_util.py:30-36, run.py:116-119)
+        self.env, self.rewards, self.needs_reset = env, None, True
+        self.episode_rewards, self.episode_lengths = [], []
+
+    def reset(self):
+        self.rewards, self.needs_reset = [], False
+        return self.env.reset()
+
+    def step(self, action):
+        assert not self.needs_reset, "Tried to step environment that needs reset"
+        ob, rew, done, info = self.env.step(action)
+        self.rewards.append(rew)
+        if done:
+            self.needs_reset = True
+            info = dict(info)
+            info["episode"] = {"r": round(sum(self.rewards), 6), "l": len(self.rewards)}
+            self.episode_rewards.append(sum(self.rewards))
+            self.episode_lengths.append(len(self.rewards))
+        return ob, rew, done, info
+
+
 class EpisodicLifeEnv:                                  # atari_wrappers.py:153-184
     def __init__(self, env, base):
         self.env, self.base, self.lives, self.was_real_done = env, base, 0, True
@@ -141,11 +163,16 @@ class WrappedEnv:
     reset-on-done (vec_env/subproc_vec_env.py:11-15).  step() returns (frames oldest-first [k,h,w], reward, done, info)."""
 
     def __init__(self, game, seed, env_id=0, frame_skip=4, noop_max=30, episode_life=True, fire_reset=True, clip_rewards=True,
-                 frame_stack=4, size=(84, 84), noop_seed=0):
+                 frame_stack=4, size=(84, 84), noop_seed=0, stack_reset="fill"):
+        """stack_reset "fill": wrap_deepmind(frame_stack=True) -- FrameStack (:246-275) owns the stack; "zero": wrap_deepmind()
+        under VecFrameStack (vec_env/vec_frame_stack.py:17-30) -- the stack of a finished env is zeroed, then holds the reset
+        observation only."""
         self.base = BaseEnv(game, seed)
         dims = O.DIMS[game]
         env = NoopResetEnv(self.base, noop_max, noop_seed, env_id) if noop_max > 0 else _PlainReset(self.base)
         self.skipper = env = MaxAndSkipEnv(env, frame_skip, (dims[1], dims[0]))
+        self.monitor = env = Monitor(env)
+        self.stack_reset = stack_reset
         if episode_life:
             env = EpisodicLifeEnv(env, self.base)
         if fire_reset and len(self.base.legal) >= 3:
@@ -156,10 +183,11 @@ class WrappedEnv:
     def _warp(self, obs):
         return warp(obs, self.size[0], self.size[1])
 
-    def reset(self):                                    # FrameStack.reset, :262-266
+    def reset(self):                                    # FrameStack.reset, :262-266 / VecFrameStack.reset, vec_frame_stack.py:27-31
         ob = self._warp(self.env.reset())
         for _ in range(self.k):
-            self.frames.append(ob)
+            self.frames.append(np.zeros_like(ob) if self.stack_reset == "zero" else ob)
+        self.frames.append(ob)
         return np.stack(self.frames)
 
     def step(self, action):
@@ -174,7 +202,10 @@ class WrappedEnv:
             stacked = self.reset()                      # the VecEnv worker: "if done: ob = env.reset()"
         else:
             stacked = np.stack(self.frames)
-        return stacked, reward, done, {"score": score, "lives": lives, "real_done": real_done, "fresh": fresh}
+        out = {"score": score, "lives": lives, "real_done": real_done, "fresh": fresh}
+        if "episode" in info:
+            out["episode"] = info["episode"]
+        return stacked, reward, done, out
 
 
 class _PlainReset:

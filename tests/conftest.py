@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# the snapshot of the reference's own unit tests is a fixture that tests/test_reference_suite.py drives with a ctoybox module
+# installed; pytest must not collect those files itself
+collect_ignore_glob = ["golden/reference_py/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

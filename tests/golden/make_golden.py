@@ -5,6 +5,11 @@ cv2 exist; the fixtures travel, the reference does not).
                                                 (toybox/interventions/defaults/), the only complete states it pins
   rng_kat.json                                  xoroshiro128+ known answers derived from those fixtures
   area_golden.npz                               cv2.resize(..., INTER_AREA) outputs for the three native frame sizes
+  reference_py/                                 byte-identical snapshot of the pure-Python reference files its own unit tests
+                                                need (toybox/interventions/*.py + defaults, toybox/envs/atari/constants.py,
+                                                test/interventions/*.py), so that tests/test_reference_suite.py can run them
+                                                on the GPU box -- where /root/reference does not exist -- against the CUDA path
+                                                (toybox_b200.ctoybox.Toybox).  Test fixtures, never imported by the product.
 """
 import json
 import os
@@ -16,7 +21,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/toybox/interventions/defaults"
 
 
+def snapshot_reference_py():
+    root = "/root/reference"
+    dst = os.path.join(HERE, "reference_py")
+    shutil.rmtree(dst, ignore_errors=True)
+    files = ["toybox/__init__.py", "toybox/envs/atari/constants.py", "test/__init__.py", "test/interventions/__init__.py"]
+    for d in ("toybox/interventions", "test/interventions"):
+        files += [os.path.join(d, f) for f in sorted(os.listdir(os.path.join(root, d))) if f.endswith(".py")]
+    files += [os.path.join("toybox/interventions/defaults", f) for f in sorted(os.listdir(os.path.join(root, "toybox/interventions/defaults")))]
+    for f in files:
+        src = os.path.join(root, f)
+        os.makedirs(os.path.dirname(os.path.join(dst, f)), exist_ok=True)
+        if os.path.exists(src):
+            shutil.copyfile(src, os.path.join(dst, f))
+        else:
+            open(os.path.join(dst, f), "w").close()          # package marker the reference does not ship
+    with open(os.path.join(dst, "README"), "w") as fh:
+        fh.write("Byte-identical copies of files of /root/reference (toybox-rs/Toybox), made by tests/golden/make_golden.py.\n"
+                 "Test fixtures only: tests/test_reference_suite.py runs the reference's own unit tests from here where the\n"
+                 "reference tree is absent (the GPU box).  Nothing under toybox_b200/ imports them.\n")
+
+
 def main():
+    snapshot_reference_py()
     for g in ("breakout", "amidar", "space_invaders"):
         for kind in ("config", "state"):
             shutil.copyfile(os.path.join(REF, "%s_%s_default.json" % (g, kind)), os.path.join(HERE, "%s_%s_default.json" % (g, kind)))

@@ -165,6 +165,80 @@ def test_direct_kernel_mixed_pool(tbx, oracle_mod):
         pool.close()
 
 
+def test_si_direct_kernel_adversarial_states(tbx, oracle_mod):
+    """Space Invaders' direct INTER_AREA kernel (sparse sprites: patches for isolated bank sprites, pixel-by-pixel evaluation
+    for the rest) on states built to hit every branch: sprites clipped by the frame, invaders moved on top of each other / of
+    shields / of lasers, eroded shields, non-default colours (no patch set), the ufo, explosions, huge lasers, lives display,
+    multi-digit scores, shields and ship pushed into the ground line -- bit-exact against the oracle, several output sizes."""
+    n = 96
+    pool, ref = _advance(tbx, oracle_mod, "space_invaders", n, 300, 21)
+    rng = np.random.default_rng(4)
+    states = []
+    for i in range(n):
+        js = ref.state_json(i)
+        k = i % 12
+        if k == 1:
+            for e in js["enemies"][:8]:
+                e["x"], e["y"] = int(rng.integers(-12, 316)), int(rng.integers(-8, 205))
+        elif k == 2:
+            for e in js["enemies"][6:18]:
+                e["x"], e["y"] = js["shields"][0]["x"] + int(rng.integers(-10, 10)), js["shields"][0]["y"] + int(rng.integers(-8, 12))
+        elif k == 3:
+            js["enemy_lasers"] = [{"x": int(rng.integers(0, 318)), "y": int(rng.integers(0, 190)), "w": 2, "h": 8, "t": 0, "movement": "Down", "speed": 3,
+                                   "color": {"r": 252, "g": 252, "b": 84, "a": 255}} for _ in range(4)]
+            js["ship_laser"] = {"x": js["enemies"][7]["x"] + 3, "y": js["enemies"][7]["y"] + 2, "w": 2, "h": 8, "t": 0, "movement": "Up", "speed": 8,
+                                "color": {"r": 35, "g": 129, "b": 59, "a": 255}}
+        elif k == 4:
+            js["ufo"]["appearance_counter"] = None
+            js["ufo"]["x"] = int(rng.integers(-2, 318))
+            js["ship"]["color"] = {"r": 200, "g": 10, "b": 90, "a": 255}
+        elif k == 5:
+            js["enemy_lasers"] = [{"x": 20, "y": 10, "w": 280, "h": 150, "t": 0, "movement": "Down", "speed": 3, "color": {"r": 9, "g": 99, "b": 199, "a": 255}}]
+        elif k == 6:
+            js["life_display_timer"] = 40
+            js["lives"] = int(rng.choice([3, 27, 104]))
+            js["score"] = int(rng.choice([0, 35, 1250, 99999, 1234567]))
+        elif k == 7:
+            for sh in js["shields"]:
+                for row in sh["data"]:
+                    for c in rng.choice(16, size=6, replace=False):
+                        row[int(c)] = {"r": 0, "g": 0, "b": 0, "a": 0}
+            js["shields"][1]["x"], js["shields"][1]["y"] = int(rng.integers(-8, 310)), int(rng.integers(170, 200))
+        elif k == 8:
+            js["ship"]["x"], js["ship"]["y"] = int(rng.integers(-10, 315)), int(rng.integers(180, 206))
+            for e in js["enemies"][:6]:
+                e["alive"] = False
+                e["death_counter"] = 5
+        elif k == 9:
+            js["ufo"]["appearance_counter"] = None
+            js["ufo"]["death_counter"] = 9
+            js["ship"]["alive"] = False
+            js["ship"]["death_counter"] = 12
+        elif k == 10:
+            for j, e in enumerate(js["enemies"]):
+                e["x"], e["y"] = 40 + 17 * (j % 12), 30 + 11 * (j // 12)          # packed: neighbours share output pixels
+        ref.write_state_json(i, js)
+        states.append(js)
+    pool.write_state_json(states)
+    legal = np.asarray(oracle_mod.LEGAL["space_invaders"], np.int32)
+    try:
+        for rnd in range(2):
+            for ow, oh in ((84, 84), (96, 80), (64, 64), (48, 60)):
+                want = ref.render("gray84", ow, oh).reshape(n, -1)
+                for v in ({}, TILE):
+                    _set_env(v)
+                    got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
+                    bad = np.argwhere(got != want)
+                    assert bad.size == 0, (rnd, ow, oh, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+            for t in range(30):
+                acts = legal[[oracle_mod.action_index(0xB200, i, 500 + t, len(legal)) for i in range(n)]]
+                pool.apply_ale_action(acts, auto_reset=True)
+                ref.step(acts, auto_reset=True)
+    finally:
+        _set_env({})
+        pool.close()
+
+
 def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
     """late-game Amidar boards (long painted corridors, painted boxes): runs of equal tiles are merged into one entry;
     every layout and renderer against the oracle"""

@@ -32,8 +32,21 @@ def test_initial_state_matches_fixture_lineage(tbx, oracle_mod, game):
     states = pool.to_state_json()
     for i in range(n):
         assert json_diff(states[i], ref.state_json(i)) == []
-    assert json_diff(pool.config_to_json(), oracle_mod.CODEC[game][2](ref.cfg)) == []
+    # config_to_json shows the simulator as it is now: its rng is the one new_game has advanced (env 0's in a pool)
+    want = oracle_mod.CODEC[game][2](ref.cfg)
+    want["rand"] = {"state": [int(ref.sim[0].s[0]), int(ref.sim[0].s[1])]}
+    assert json_diff(pool.config_to_json(), want) == []
+    one = oracle_mod.OracleToybox(game)                      # ... which is what the batch-1 ctoybox look-alike reports
+    assert json_diff(pool.config_to_json(), one.config_to_json()) == []
     check_frames(pool, ref, n)
+    # write_config_json replaces the simulator, rng included: the next new_game starts the same lineage again
+    cfg = pool.config_to_json()
+    pool.write_config_json(cfg)
+    pool.new_game()
+    one.write_config_json(cfg)
+    one.new_game()
+    assert json_diff(pool.to_state_json([n - 1])[0], one.to_state_json()) == []
+    assert json_diff(pool.config_to_json(), one.config_to_json()) == []
     pool.close()
 
 
@@ -128,6 +141,29 @@ def test_json_round_trip_and_intervention(tbx, oracle_mod, game):
     for i in range(n):
         assert json_diff(pool.to_state_json([i])[0], ref.state_json(i)) == [], i
     pool.close()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_step_random_equals_fill_then_step(tbx, oracle_mod, game):
+    """tbx_step_random (the synthetic stream generated inside the step kernel) == tbx_fill_actions + tbx_step, and both follow
+    the oracle driven by the CPU restatement of the stream"""
+    import torch
+    n = 37
+    a = tbx.BatchedToybox(game, n, seeds=11)
+    b = tbx.BatchedToybox(game, n, seeds=11)
+    ref = oracle_mod.OracleBatch(game, n, seeds=11 + np.arange(n))
+    acts = torch.empty(n, dtype=torch.int32, device=a.device)
+    legal = np.asarray(oracle_mod.LEGAL[game], np.int32)
+    for t in range(300):
+        a.step_random(0xB200, t, env0=5, auto_reset=True)
+        b.fill_random_actions(acts, 0xB200, t, 5)
+        b.apply_ale_action(acts, auto_reset=True)
+        r, d, s, l = ref.step(legal[[oracle_mod.action_index(0xB200, 5 + i, t, len(legal)) for i in range(n)]], auto_reset=True)
+        for pool in (a, b):
+            assert np.array_equal(pool.score.cpu().numpy(), s) and np.array_equal(pool.lives.cpu().numpy(), l), t
+            assert np.array_equal(pool.reward.cpu().numpy(), r) and np.array_equal(pool.done.cpu().numpy().astype(bool), d), t
+    assert a.to_state_json([0, n - 1]) == b.to_state_json([0, n - 1])
+    a.close(); b.close()
 
 
 def test_ragged_batch_sizes_and_invalid_action(tbx, oracle_mod):

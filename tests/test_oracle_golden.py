@@ -141,34 +141,3 @@ def test_area_resize_equals_live_cv2(oracle_mod):
             got = np.empty((84, 84), np.uint8)
             L.tbo_resize_area_u8(src.ctypes.data_as(C.c_void_p), w, h, 1, got.ctypes.data_as(C.c_void_p), 84, 84)
             assert np.array_equal(got, cv2.resize(src, (84, 84), interpolation=cv2.INTER_AREA))
-
-
-@pytest.mark.parametrize("game", ["breakout", "amidar", "space_invaders"])
-def test_ctoybox_trace(oracle_mod, game):
-    """replay a trace recorded from a real ctoybox (tools/record_golden_trace.py) on the oracle.  No trace
-    can be recorded in this image (ctoybox is absent), so until one is committed this only checks the recorder's
-    restatement of the action stream against the library's."""
-    import hashlib
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("record_golden_trace", os.path.join(os.path.dirname(os.path.dirname(GOLD)), "tools", "record_golden_trace.py"))
-    rec = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(rec)
-    n_legal = len(oracle_mod.LEGAL[game])
-    assert list(oracle_mod.LEGAL[game]) == rec.LEGAL[game]
-    for t in (0, 1, 7, 1000, 123456):
-        for env in (0, 5):
-            assert rec.action_index(0xB200, env, t, n_legal) == oracle_mod.action_index(0xB200, env, t, n_legal)
-    path = os.path.join(GOLD, "ctoybox_trace_%s.json" % game)
-    if not os.path.exists(path):
-        pytest.skip("no ctoybox trace recorded (ctoybox==0.5.0 is not installable here): transition/raster parity stays unpinned")
-    trace = json.load(open(path))
-    b = oracle_mod.OracleBatch(game, 1, seeds=np.asarray([trace["seed"]], np.uint32))
-    recs = {r["t"]: r for r in trace["records"]}
-    legal = trace["legal"]
-    for t in range(max(recs) + 1):
-        if t in recs:
-            r = recs[t]
-            assert json_diff(b.state_json(0), r["state"]) == [], t
-            assert hashlib.sha256(b.render("rgba")[0].tobytes()).hexdigest() == r["rgba_sha256"], t
-            assert hashlib.sha256(b.render("gray")[0].tobytes()).hexdigest() == r["gray_sha256"], t
-        b.step(np.asarray([legal[rec.action_index(trace["action_seed"], 0, t, len(legal))]], np.int32), auto_reset=False)

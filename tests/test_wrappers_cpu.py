@@ -28,6 +28,31 @@ def test_wrapper_chain_properties(oracle_mod):
     assert dones > 0                                                         # random play loses lives: EpisodicLife episodes
 
 
+def test_vec_frame_stack_and_monitor_restatement(oracle_mod):
+    """stack_reset="zero" follows VecFrameStack (vec_env/vec_frame_stack.py:17-30): zeros + the reset observation; the Monitor
+    restatement (bench/monitor.py:58-76) counts MaxAndSkipEnv steps and raw rewards between real resets"""
+    from oracle import wrappers as OW
+    env = OW.WrappedEnv("breakout", 11, env_id=0, noop_seed=3, stack_reset="zero", clip_rewards=False)
+    obs = env.reset()
+    assert not obs[:3].any() and obs[3].any()
+    steps_since_reset, ret, episodes = 2, 0, 0           # FireResetEnv.reset made two MaxAndSkip steps below the agent
+    for t in range(1500):
+        stacked, r, d, info = env.step(1 if t % 7 == 0 else 2 + t % 2)
+        steps_since_reset += 1
+        ret += r
+        if d:
+            assert not stacked[:3].any() and stacked[3].any()
+            if info["real_done"]:
+                assert info["episode"] == {"r": ret, "l": steps_since_reset}
+                episodes += 1
+                steps_since_reset, ret = 2, 0
+            else:
+                steps_since_reset += 3                   # EpisodicLifeEnv's NOOP step + FireResetEnv's FIRE and RIGHT steps
+        else:
+            assert "episode" not in info
+    assert episodes > 0
+
+
 def test_max_and_skip_matches_manual_frames(oracle_mod):
     """MaxAndSkipEnv over the oracle: 4 frames of one action, observation = max of the states after frames 3 and 4"""
     from oracle import oracle as O

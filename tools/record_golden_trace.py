@@ -5,8 +5,9 @@ wheel is available (it is not in this image: third-party Rust crate ctoybox==0.5
 Pattern: scripts/utils/start_images_toybox:24-37 (seed 1234, step, save frames).  For each game: set_seed(1234),
 new_game(), then `--steps` frames of the library's counter-based action stream (seed 0xB200, env 0); every
 `--every` frames the state JSON and the SHA-256 of the RGBA and grayscale frames are written to
-tests/golden/ctoybox_trace_<game>.json.  tests/test_oracle_golden.py::test_ctoybox_trace replays the same actions on
-the oracle and compares whenever such a file exists.
+tests/golden/ctoybox_trace_<game>.json.  tests/test_golden_trace.py replays the same actions (`replay` below) on the oracle,
+on the host build of the product's engines and -- GPU tier -- on the CUDA path, and compares whenever such a file exists;
+it also proves this recorder / replayer pair on traces recorded from those three implementations themselves.
 
     python tools/record_golden_trace.py [--steps 2000] [--every 50] [--out tests/golden]
 """
@@ -48,6 +49,42 @@ def record(game, steps, every, make):
         if t < steps:
             tb.apply_ale_action(legal[action_index(0xB200, 0, t, len(legal))])
     return trace
+
+
+def _numbers_equal(a, b):
+    """JSON documents compare by value (1 == 1.0), dict order ignored"""
+    if isinstance(a, dict) and isinstance(b, dict):
+        return a.keys() == b.keys() and all(_numbers_equal(a[k], b[k]) for k in a)
+    if isinstance(a, list) and isinstance(b, list):
+        return len(a) == len(b) and all(_numbers_equal(x, y) for x, y in zip(a, b))
+    if isinstance(a, bool) or isinstance(b, bool):
+        return a is b
+    return a == b
+
+
+def replay(trace, make):
+    """Replay `trace` on the ctoybox-compatible Toybox that make(game) returns; a list of (t, what) mismatches, empty = parity."""
+    tb = make(trace["game"])
+    tb.set_seed(trace["seed"])
+    tb.new_game()
+    recs = {r["t"]: r for r in trace["records"]}
+    legal = trace["legal"]
+    bad = []
+    for t in range(max(recs) + 1):
+        if t in recs:
+            r = recs[t]
+            if not _numbers_equal(tb.to_state_json(), r["state"]):
+                bad.append((t, "state"))
+            if (tb.get_score(), tb.get_lives()) != (r["score"], r["lives"]):
+                bad.append((t, "score/lives"))
+            tb.grayscale = False
+            if hashlib.sha256(tb.get_state().tobytes()).hexdigest() != r["rgba_sha256"]:
+                bad.append((t, "rgba frame"))
+            tb.grayscale = True
+            if hashlib.sha256(tb.get_state().tobytes()).hexdigest() != r["gray_sha256"]:
+                bad.append((t, "gray frame"))
+        tb.apply_ale_action(legal[action_index(trace["action_seed"], 0, t, len(legal))])
+    return bad
 
 
 def main():

@@ -84,6 +84,7 @@ def lib():
         "tbx_new_game": (i32, [vp, vp, vp]),
         "tbx_step": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
         "tbx_step_inputs": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
+        "tbx_step_random": (i32, [vp, u64, u64, u64, i32, vp, vp, vp, vp, vp]),
         "tbx_check": (i32, [vp, vp]),
         "tbx_render": (i32, [vp, vp, i32, i32, i32, vp]),
         "tbx_read_scalars": (i32, [vp, vp, vp, vp, vp]),
@@ -98,6 +99,7 @@ def lib():
         "tbx_free_str": (None, [vp]),
         "tbx_stats_read": (i32, [vp, vp, i32, vp]),
         "tbx_stats_read_device": (i32, [vp, vp, vp]),
+        "tbx_breakout_columns": (i32, [vp, i32, i32, vp, vp, vp]),
         "tbx_fill_actions": (i32, [vp, vp, u64, u64, u64, vp]),
         "tbx_fill_actions_at": (i32, [vp, vp, u64, u64, vp, vp]),
         "tbx_fill_actions_policy": (i32, [vp, vp, i32, u64, vp]),
@@ -106,6 +108,8 @@ def lib():
         "tbx_field_set": (i32, [vp, cp, vp, vp, vp]),
         "tbx_wrap_create": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, u64, u64, C.POINTER(vp)]),
         "tbx_wrap_destroy": (i32, [vp]),
+        "tbx_wrap_set_stack_mode": (i32, [vp, i32]),
+        "tbx_wrap_set_episode_outputs": (i32, [vp, vp, vp]),
         "tbx_wrap_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]),
     }
     for name, (res, args) in sigs.items():
@@ -121,7 +125,7 @@ EXPORTS = ["tbx_last_error", "tbx_version", "tbx_pool_create", "tbx_pool_destroy
            "tbx_step_inputs", "tbx_check", "tbx_render", "tbx_read_scalars", "tbx_step_host", "tbx_state_to_json",
            "tbx_state_from_json", "tbx_config_to_json", "tbx_config_from_json", "tbx_schema_for_state", "tbx_schema_for_config",
            "tbx_query_json", "tbx_free_str", "tbx_stats_read", "tbx_fill_actions", "tbx_fill_actions_policy",
-           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set", "tbx_fill_actions_at", "tbx_stats_read_device"]
+           "tbx_wrap_create", "tbx_wrap_destroy", "tbx_wrap_step", "tbx_field_lookup", "tbx_field_get", "tbx_field_set", "tbx_fill_actions_at", "tbx_stats_read_device", "tbx_wrap_set_stack_mode", "tbx_wrap_set_episode_outputs", "tbx_breakout_columns", "tbx_step_random"]
 
 
 def check(rc):

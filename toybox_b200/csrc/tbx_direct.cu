@@ -9,15 +9,30 @@ using namespace tbxk;
 static int align16(int v) { return (v + 15) & ~15; }
 
 cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, const tbx::ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray,
-                             void **d_aux) {
+                             void **d_aux, void **d_aux2) {
   *d_aux = 0;
+  *d_aux2 = 0;
+  cudaError_t e = cudaSuccess;
   if (c.game == TBX_BREAKOUT && brk_default) {
     std::vector<TbxBrkDirect> aux(1);
     tbx::build_brk_direct(c, *brk_default, rs, plan, base0_gray, aux[0]);
     if (!aux[0].ok) return cudaSuccess;
-    cudaError_t e = cudaMalloc(d_aux, sizeof(TbxBrkDirect));
+    e = cudaMalloc(d_aux, sizeof(TbxBrkDirect));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*d_aux, aux.data(), sizeof(TbxBrkDirect), cudaMemcpyHostToDevice);
+  }
+  if (c.game == TBX_SPACE_INVADERS) {
+    std::vector<TbxSiDirect> aux(1);
+    std::vector<TbxSpritePatch> patches;
+    tbx::build_si_direct(c, rs, plan, base0_gray, aux[0], patches);
+    if (!aux[0].ok) return cudaSuccess;
+    e = cudaMalloc(d_aux, sizeof(TbxSiDirect));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(*d_aux, aux.data(), sizeof(TbxSiDirect), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess || patches.empty()) return e;
+    e = cudaMalloc(d_aux2, patches.size() * sizeof(TbxSpritePatch));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d_aux2, patches.data(), patches.size() * sizeof(TbxSpritePatch), cudaMemcpyHostToDevice);
   }
   return cudaSuccess;
 }
@@ -25,35 +40,68 @@ cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, 
 void tbx_direct_geometry(int game, int out_w, int out_h, DirectArgs &d) {
   d.hstride = (out_w + 3) & ~3;
   d.smem_base = align16(out_w * out_h);
-  /* per warp: its env's record, the wall's H rows, the movers' records */
-  d.warp_bytes = game == TBX_BREAKOUT ? align16(TBX_WORDS(BrkRec) * 4) + align16(TBX_BRK_MAX_ROWS * d.hstride * (int)sizeof(float)) + 256 : 0;
-  d.smem_total = d.smem_base + 2 * TBX_WORDS(BrkRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
+  if (game == TBX_BREAKOUT) {
+    /* per warp: its env's record, the wall's H rows, the movers' records; two record stages */
+    d.warp_bytes = align16(TBX_WORDS(BrkRec) * 4) + align16(TBX_BRK_MAX_ROWS * d.hstride * (int)sizeof(float)) + 256;
+    d.smem_total = d.smem_base + 2 * TBX_WORDS(BrkRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
+  } else {
+    /* per warp: its env's record, the entries, two coverage bitmaps, the evaluated-entry list; one record stage */
+    const int ow = (out_w + 31) / 32;
+    d.warp_bytes = align16(TBX_WORDS(SiRec) * 4) + TBX_SD_MAX_ENTRIES * 32 + align16(2 * out_h * ow * 4) + TBX_SD_MAX_ENTRIES * 8;
+    d.smem_total = d.smem_base + TBX_WORDS(SiRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
+  }
 }
 
-template <int TX, int TY> static cudaError_t launch_brk(const RenderArgs &a, const BrkCfg &cfg, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
-  /* the attribute is per device: set it on every launch (a cheap host-side call) rather than caching it per process */
-  cudaError_t e = cudaFuncSetAttribute(brk_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
-  if (e != cudaSuccess) return e;
-  /* persistent grid: as many CTAs as the device keeps resident (cached per device), each walks its share of the chunks */
+/* persistent grid: as many CTAs as the device keeps resident (cached per device and kernel), each walks its share of the chunks */
+template <class K> static cudaError_t persistent_grid(K kernel, int smem, int n_chunks, int *grid_out) {
   static int resident[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!resident[dev]) {
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brk_direct_kernel<TX, TY>, TBX_DIRECT_THREADS, d.smem_total);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TBX_DIRECT_THREADS, smem);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     resident[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
   }
-  const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
   int grid = n_chunks < resident[dev] ? n_chunks : resident[dev];
   if (const char *env = getenv("TBX_DIRECT_GRID")) if (atoi(env) > 0) grid = atoi(env) < n_chunks ? atoi(env) : n_chunks; /* tuning / tests */
+  *grid_out = grid;
+  return cudaSuccess;
+}
+
+template <int TX, int TY> static cudaError_t launch_brk(const RenderArgs &a, const BrkCfg &cfg, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
+  /* the attribute is per device: set it on every launch (a cheap host-side call) rather than caching it per process */
+  cudaError_t e = cudaFuncSetAttribute(brk_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
+  if (e != cudaSuccess) return e;
+  int grid = 1;
+  e = persistent_grid(brk_direct_kernel<TX, TY>, d.smem_total, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
+  if (e != cudaSuccess) return e;
   brk_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, d.smem_total, s>>>(a, cfg, plan, d);
+  return cudaGetLastError();
+}
+template <int TX, int TY> static cudaError_t launch_si(const RenderArgs &a, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(si_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
+  if (e != cudaSuccess) return e;
+  int grid = 1;
+  e = persistent_grid(si_direct_kernel<TX, TY>, d.smem_total, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
+  if (e != cudaSuccess) return e;
+  si_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, d.smem_total, s>>>(a, plan, d);
   return cudaGetLastError();
 }
 
 cudaError_t tbx_launch_direct(int game, int tx, int ty, const RenderArgs &a, const void *cfg_host, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
+  if (game == TBX_SPACE_INVADERS) {
+    if (ty <= 3) {
+      if (tx <= 3) return launch_si<3, 3>(a, plan, d, s);
+      if (tx <= 4) return launch_si<4, 3>(a, plan, d, s);
+      return launch_si<5, 3>(a, plan, d, s);
+    }
+    if (tx <= 3) return launch_si<3, 4>(a, plan, d, s);
+    if (tx <= 4) return launch_si<4, 4>(a, plan, d, s);
+    return launch_si<5, 4>(a, plan, d, s);
+  }
   if (game != TBX_BREAKOUT) return cudaErrorInvalidValue;
   const BrkCfg &cfg = *(const BrkCfg *)cfg_host;
   if (ty <= 3) {

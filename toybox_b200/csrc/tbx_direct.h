@@ -143,4 +143,34 @@ TBX_HD int tbx_digit_at(int value, int k) {
   return (int)(q % 10u);
 }
 
+/* ------------------------------------------------------------------ sparse sprites on a plain base (Space Invaders)
+ * The frame is the base frame (black + ground line) plus ~50 small entries of the draw list.  An entry whose output
+ * footprint meets no other entry's ("simple") and lies on plain background is the only thing that differs from the base
+ * there: if it is a 16-bit-wide bank sprite at scale 1 in one of its usual colours, its output pixels are a PRE-RESOLVED
+ * PATCH that depends on the sprite and on (x mod px_period, y mod py_period) only -- INTER_AREA's tap pattern repeats
+ * every px_period source columns / py_period source rows (84 x 84 from 320 x 210: 80 and 5).  Everything else (shields,
+ * whose bits live in the state; lasers; entries that touch each other) is evaluated pixel by pixel: the TX x TY source
+ * window is built as packed bytes from the base frame and the non-simple entries in draw order, then resolved in cv2's
+ * tap order. */
+#define TBX_SD_MAX_ENTRIES 72
+#define TBX_SD_MAX_SETS 16
+#define TBX_SP_MAX_W 6
+#define TBX_SP_MAX_H 5
+typedef struct TbxSpritePatch { uint8_t w, h; uint8_t px[TBX_SP_MAX_W * TBX_SP_MAX_H]; } TbxSpritePatch; /* 32 bytes; pixel (r, c) at px[r * TBX_SP_MAX_W + c] */
+typedef struct TbxSiDirect {
+  int32_t ok;
+  int32_t n_sets;                /* (sprite, gray) pairs with patch tables; 0: no patches (every entry is evaluated) */
+  int32_t px_period, py_period;  /* source period of the tap pattern per axis */
+  int32_t ox_period, oy_period;  /* output pixels per period */
+  int32_t bg_gray, _pad;
+  uint32_t inv_px, inv_py;       /* ceil(2^32 / period) (0 when the period is 1): v / period == umulhi(v, inv) for coordinates */
+  uint16_t set_off[TBX_SD_MAX_SETS];  /* bank offset of the set's sprite */
+  uint8_t set_gray[TBX_SD_MAX_SETS];
+  uint8_t set_h[TBX_SD_MAX_SETS];     /* sprite rows (10; ufo 7) */
+  uint8_t set_lut[16][4];             /* per bank sprite ((off - 50) / 10, explosions 8 + (off - 127) / 10): up to 4 candidate sets, 255 = none */
+  uint32_t inv32[TBX_AREA_MAX_DST + 1]; /* ceil(2^32 / n) for n >= 2 */
+  uint32_t plain[TBX_AREA_MAX_DST][4]; /* per output row: the output columns all of whose real taps are background in base frame 0 */
+} TbxSiDirect;
+/* patch of set s at phase (x mod px_period, y mod py_period): patches[(s * py_period + yphase) * px_period + xphase] */
+
 #endif

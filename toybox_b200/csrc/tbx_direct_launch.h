@@ -7,7 +7,8 @@
 
 namespace tbxk {
 struct DirectArgs {
-  const void *aux;    /* the game's closed-form tables on the device (TbxBrkDirect ...) */
+  const void *aux;    /* the game's closed-form tables on the device (TbxBrkDirect, TbxSiDirect) */
+  const void *aux2;   /* Space Invaders: the sprite patch tables (TbxSpritePatch[]) */
   int32_t *fb_list;   /* envs handed to the tile kernel */
   int *fb_count;
   int hstride;        /* floats per H row in shared memory */
@@ -19,7 +20,7 @@ struct DirectArgs {
 
 /* closed-form tables of one (config, output size) pair on the device; *d_aux stays NULL when the pair is not covered */
 cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, const tbx::ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray,
-                             void **d_aux);
+                             void **d_aux, void **d_aux2);
 /* shared memory per warp / floats per H row for an output width */
 void tbx_direct_geometry(int game, int out_w, int out_h, tbxk::DirectArgs &d);
 /* direct INTER_AREA kernel instantiated for at least tx x ty taps (tx <= 5, ty <= 4) */

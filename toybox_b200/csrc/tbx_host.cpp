@@ -1032,4 +1032,84 @@ void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, c
   A.ok = 1;
 }
 
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+/* Space Invaders: the sprite patch tables and the plain-background map of one output size (tbx_direct.h).  `patches`
+ * receives n_sets * py_period * px_period entries (empty when the tables would be too large: n_sets = 0). */
+void build_si_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &pl, const uint8_t *base0, TbxSiDirect &A, std::vector<TbxSpritePatch> &patches) {
+  memset(&A, 0, sizeof A);
+  patches.clear();
+  const int W = TBX_SI_W, H = TBX_SI_H, dw = pl.dw, dh = pl.dh;
+  if (c.game != TBX_SPACE_INVADERS || dw % 4 != 0 || dw > TBX_AREA_MAX_DST || dh > TBX_AREA_MAX_DST || pl.tx > 5 || pl.ty > 4) return;
+  A.bg_gray = (int32_t)tbx_luma(SI_COLOR_BLACK);
+  /* plain output pixels: every real tap reads background in base frame 0 */
+  for (int dy = 0; dy < dh; dy++)
+    for (int dx = 0; dx < dw; dx++) {
+      bool plain = true;
+      for (int ky = rs.y.start[dy]; ky < rs.y.start[dy + 1] && plain; ky++)
+        for (int kx = rs.x.start[dx]; kx < rs.x.start[dx + 1]; kx++)
+          if (base0[(size_t)rs.y.si[ky] * W + rs.x.si[kx]] != (uint8_t)A.bg_gray) { plain = false; break; }
+      if (plain) A.plain[dy][dx >> 5] |= 1u << (dx & 31);
+    }
+  A.px_period = W / gcd_int(W, dw); A.ox_period = dw / gcd_int(W, dw);
+  A.py_period = H / gcd_int(H, dh); A.oy_period = dh / gcd_int(H, dh);
+  for (int k = 2; k <= TBX_AREA_MAX_DST; k++) A.inv32[k] = 0xffffffffu / (uint32_t)k + 1u;
+  A.inv_px = A.px_period > 1 ? 0xffffffffu / (uint32_t)A.px_period + 1u : 0u;
+  A.inv_py = A.py_period > 1 ? 0xffffffffu / (uint32_t)A.py_period + 1u : 0u;
+  A.ok = 1;
+  /* the patches rely on the tap tables repeating exactly (start offsets and f32 weights, bit for bit): check, do not assume */
+  for (int dx = 0; dx + A.ox_period < dw; dx++) {
+    if (pl.xs0[dx + A.ox_period] != pl.xs0[dx] + A.px_period) return;
+    for (int t = 0; t < TBX_AREA_MAX_TAPS; t++) if (memcmp(&pl.xalpha[t][dx + A.ox_period], &pl.xalpha[t][dx], sizeof(float)) != 0) return;
+  }
+  for (int dy = 0; dy + A.oy_period < dh; dy++) {
+    if (pl.ys0[dy + A.oy_period] != pl.ys0[dy] + A.py_period) return;
+    for (int t = 0; t < TBX_AREA_MAX_TAPS; t++) if (memcmp(&pl.yalpha[t][dy + A.oy_period], &pl.yalpha[t][dy], sizeof(float)) != 0) return;
+  }
+  /* (sprite, colour) pairs of the draw list's 16-pixel-wide bank sprites at scale 1 (si_prim) */
+  struct Set { int off, h; uint32_t color; };
+  std::vector<Set> sets;
+  for (int k = 0; k < 6; k++) sets.push_back({TBX_BANK_INVADER + 10 * k, SI_ENEMY_H, SI_COLOR_ENEMY});
+  sets.push_back({TBX_BANK_BOOM, SI_ENEMY_H, SI_COLOR_ENEMY});
+  sets.push_back({TBX_BANK_SHIP, SI_ENEMY_H, SI_COLOR_SHIP});
+  sets.push_back({TBX_BANK_BOOM, SI_ENEMY_H, SI_COLOR_SHIP});
+  sets.push_back({TBX_BANK_BOOM + 10, SI_ENEMY_H, SI_COLOR_SHIP});
+  sets.push_back({TBX_BANK_UFO, SI_UFO_H, SI_COLOR_UFO});
+  sets.push_back({TBX_BANK_BOOM + 10, SI_ENEMY_H, SI_COLOR_UFO});
+  const size_t n_phase = (size_t)A.px_period * A.py_period;
+  if (sets.size() > TBX_SD_MAX_SETS || n_phase * sets.size() * sizeof(TbxSpritePatch) > ((size_t)4 << 20)) return; /* no patches: every entry is evaluated */
+  /* a phase must have room: the sprite at (xp, yp), fully inside a frame-sized canvas of background */
+  std::vector<uint8_t> canvas((size_t)W * H);
+  std::vector<TbxSpritePatch> out(n_phase * sets.size());
+  for (size_t s = 0; s < sets.size(); s++) {
+    const uint8_t g = (uint8_t)tbx_luma(sets[s].color);
+    for (int yp = 0; yp < A.py_period; yp++)
+      for (int xp = 0; xp < A.px_period; xp++) {
+        /* any position with this phase gives the same patch (that is what the period means); take one inside the frame */
+        int x = xp, y = yp;
+        while (x + 16 > W) x -= A.px_period;
+        while (y + sets[s].h > H) y -= A.py_period;
+        if (x < 0 || y < 0) return; /* frame smaller than a period + sprite: no patches */
+        std::fill(canvas.begin(), canvas.end(), (uint8_t)A.bg_gray);
+        for (int r = 0; r < sets[s].h; r++)
+          for (int q = 0; q < 16; q++)
+            if ((HOST_BANK[sets[s].off + r] >> (15 - q)) & 1u) canvas[(size_t)(y + r) * W + x + q] = g;
+        const int dx0 = pl.xdlo[x], dx1 = pl.xdhi[x + 15], dy0 = pl.ydlo[y], dy1 = pl.ydhi[y + sets[s].h - 1];
+        const int w = dx1 - dx0 + 1, h = dy1 - dy0 + 1;
+        if (w > TBX_SP_MAX_W || h > TBX_SP_MAX_H) return; /* footprint larger than a patch holds: no patches */
+        TbxSpritePatch &P = out[(s * A.py_period + yp) * A.px_period + xp];
+        P.w = (uint8_t)w; P.h = (uint8_t)h;
+        for (int r = 0; r < h; r++)
+          for (int q = 0; q < w; q++) P.px[r * TBX_SP_MAX_W + q] = area_pixel(canvas.data(), W, rs, dx0 + q, dy0 + r);
+      }
+  }
+  A.n_sets = (int32_t)sets.size();
+  memset(A.set_lut, 255, sizeof A.set_lut);
+  for (size_t s = 0; s < sets.size(); s++) {
+    const int idx = sets[s].off >= TBX_BANK_BOOM ? 8 + (sets[s].off - TBX_BANK_BOOM) / 10 : (sets[s].off - TBX_BANK_INVADER) / 10;
+    for (int k = 0; k < 4; k++) if (A.set_lut[idx][k] == 255) { A.set_lut[idx][k] = (uint8_t)s; break; }
+  }
+  for (size_t s = 0; s < sets.size(); s++) { A.set_off[s] = (uint16_t)sets[s].off; A.set_gray[s] = (uint8_t)tbx_luma(sets[s].color); A.set_h[s] = (uint8_t)sets[s].h; }
+  patches.swap(out);
+}
+
 } /* namespace tbx */

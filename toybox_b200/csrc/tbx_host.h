@@ -10,6 +10,8 @@
 #include <vector>
 
 struct TbxBrkDirect; /* tbx_direct.h */
+struct TbxSiDirect;
+struct TbxSpritePatch;
 
 namespace tbx {
 
@@ -86,6 +88,8 @@ void build_digit_patches(const Config &c, const BrkTable *brk_default, const Res
 /* closed-form tables of the direct INTER_AREA kernel (tbx_direct.h) for the config's default brick table and one output
  * size; out.ok == 0 when the pair is outside its limits (irregular brick grid, output width not a multiple of 4 ...) */
 void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray, TbxBrkDirect &out);
+/* Space Invaders: plain-background map and pre-resolved sprite patch tables of the direct kernel (tbx_direct.h) */
+void build_si_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray, TbxSiDirect &out, std::vector<TbxSpritePatch> &patches);
 int digit_slot0(int game);   /* first draw-list slot of the HUD digit fields */
 int digit_slots(int game);   /* how many consecutive digit slots follow */
 

@@ -19,6 +19,11 @@ struct StepArgs {
   const void *cfg, *tables;
   const int32_t *actions; /* ALE ids, or NULL */
   const uint8_t *inputs;  /* Input bitmasks, or NULL */
+  /* both NULL: the benchmark's synthetic stream, generated in the kernel (no separate launch): env i takes
+   * legal[tbx_action_index(syn_seed, syn_env0 + i, syn_t, n_legal)] */
+  const int32_t *legal;
+  int n_legal;
+  uint64_t syn_seed, syn_env0, syn_t;
   int auto_reset;
   int32_t *reward, *score, *lives;
   uint8_t *done;
@@ -26,17 +31,31 @@ struct StepArgs {
   int *bad_actions;
 };
 
+/* Thread per env.  The env's record is STAGED IN SHARED MEMORY first: between two steps the render kernel writes hundreds of MB
+ * of observations, so the state planes are no longer in L2, and a transition that reads them field by field is a chain of
+ * dependent DRAM round trips (measured: 86 cycles per warp instruction, 11 % issue-active).  Staged, every state word of the
+ * block travels in one burst of independent, coalesced loads (word w of 32 consecutive envs = one 128-byte line); the transition
+ * then runs on shared memory (column `tid`, stride EPB words: conflict-free) and only the words it changed are written back. */
+template <int GAME> struct StepGeom { static constexpr int EPB = Traits<GAME>::RW * 128 * 4 <= 48 * 1024 ? 128 : Traits<GAME>::RW * 64 * 4 <= 64 * 1024 ? 64 : 32; };
 template <int GAME>
-__global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(StepGeom<GAME>::EPB) step_kernel(StepArgs a) {
   typedef Traits<GAME> T;
-  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int EPB = StepGeom<GAME>::EPB, RW = T::RW;
+  extern __shared__ uint32_t srec[]; /* [RW][EPB] */
+  const int tid = threadIdx.x, env = blockIdx.x * EPB + tid;
   if (env >= a.n) return;
+  const uint32_t *gcol = a.planes + env;
+  uint32_t *scol = srec + tid;
+#pragma unroll 8
+  for (int w = 0; w < RW; w++) scol[w * EPB] = gcol[(size_t)w * a.n_pad];
   TbxAcc S;
-  S.p = a.planes + env;
-  S.stride = (size_t)a.n_pad;
+  S.p = scol;
+  S.stride = (size_t)EPB;
   const typename T::Cfg &cfg = *(const typename T::Cfg *)a.cfg;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
-  int in = a.actions ? tbx_ale_action_to_input(a.actions[env]) : (int)a.inputs[env];
+  int in = a.actions ? tbx_ale_action_to_input(a.actions[env])
+           : a.inputs ? (int)a.inputs[env]
+                      : tbx_ale_action_to_input(a.legal[tbx_action_index(a.syn_seed, a.syn_env0 + (uint64_t)env, a.syn_t, (uint32_t)a.n_legal)]);
   int lives_before = S.ldi(TBX_HW(lives));
   if (in < 0) atomicAdd(a.bad_actions, 1);
   else T::step(S, cfg, tables, in);
@@ -52,6 +71,13 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
     atomicMax((long long *)(a.stats + 3), (long long)o.ep_return);
   }
   if (o.done && a.auto_reset) T::new_game(S, cfg, tables);
+  /* write back what changed (the planes' lines are in L2 now: the compare costs no DRAM traffic) */
+  uint32_t *wcol = a.planes + env;
+#pragma unroll 8
+  for (int w = 0; w < RW; w++) {
+    const uint32_t v = scol[w * EPB];
+    if (v != wcol[(size_t)w * a.n_pad]) wcol[(size_t)w * a.n_pad] = v;
+  }
 }
 
 template <int GAME>
@@ -143,6 +169,32 @@ __global__ void field_set_kernel(uint32_t *planes, int n, int n_pad, int word, i
     *p = (uint32_t)val_i[env];
     if (also_word >= 0) planes[(size_t)also_word * n_pad + env] = (uint32_t)val_i[env]; /* score: prev_score follows, as write_state_json does */
   }
+}
+
+/* BreakoutIntervention.add_channel / fill_column (toybox/interventions/breakout.py:406-416) and ctoybox's channel count for every
+ * (masked) env, straight on the alive-mask words: op 0 = every brick of column `col` dead, 1 = alive again, 2 = out[env] = number
+ * of columns with no alive brick.  A brick's column is the `col` field of the env's OWN brick table (envs whose bricks were edited
+ * through JSON carry their own), columns 0..63 as in query_state_json('count_channels'). */
+__global__ void brk_column_kernel(uint32_t *planes, int n, int n_pad, const BrkTable *tables, int op, int col, const uint8_t *mask, int32_t *out) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n || (op != 2 && mask && !mask[env])) return;
+  const BrkTable &T = tables[(int32_t)planes[(size_t)TBX_HW(tbl) * n_pad + env]];
+  uint32_t alive[5];
+  for (int k = 0; k < 5; k++) alive[k] = planes[(size_t)(BRK_W(alive) + k) * n_pad + env];
+  if (op == 2) {
+    unsigned long long has = 0, live = 0;
+    for (int i = 0; i < T.n_bricks; i++) {
+      const int c = T.col[i];
+      if (c < 0 || c > 63) continue;
+      has |= 1ull << c;
+      if ((alive[i >> 5] >> (i & 31)) & 1u) live |= 1ull << c;
+    }
+    out[env] = __popcll(has & ~live);
+    return;
+  }
+  for (int i = 0; i < T.n_bricks; i++)
+    if (T.col[i] == col) { if (op) alive[i >> 5] |= 1u << (i & 31); else alive[i >> 5] &= ~(1u << (i & 31)); }
+  for (int k = 0; k < 5; k++) planes[(size_t)(BRK_W(alive) + k) * n_pad + env] = alive[k];
 }
 
 /* records (AoS, rw words each) <-> planes, for the JSON import/export of a few envs */

@@ -25,7 +25,7 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
 
 struct AreaRes {
   TbxAreaPlan *d_plan; TbxAreaPlan plan; uint8_t *d_base_out[2]; TbxDigitPatch *d_patches[2]; int dw, dh, tx, ty;
-  void *d_direct; int direct_ok; /* closed-form tables of the direct kernel (tbx_direct.h), NULL / 0 when the pair is not covered */
+  void *d_direct, *d_direct2; int direct_ok; /* tables of the direct kernel (tbx_direct.h), NULL / 0 when the pair is not covered */
 };
 static void drop_render_cache(struct tbx_pool *p);
 
@@ -115,6 +115,13 @@ static void install_default_table(tbx_pool *p) {
 
 template <int GAME> static void launch_new_game(tbx_pool *p, const uint8_t *mask, cudaStream_t s) {
   new_game_kernel<GAME><<<blocks(p->n, 128), 128, 0, s>>>(p->planes, p->n, p->n_pad, p->d_cfg, p->d_tables, mask);
+}
+template <int GAME> static int launch_step(tbx_pool *p, const StepArgs &a, cudaStream_t s) {
+  constexpr int EPB = StepGeom<GAME>::EPB, smem = Traits<GAME>::RW * EPB * 4; /* the block's records, staged (tbx_kernels.cuh) */
+  CK((cudaFuncSetAttribute(step_kernel<GAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+  step_kernel<GAME><<<blocks(p->n, EPB), EPB, smem, s>>>(a);
+  CK(cudaGetLastError());
+  return TBX_OK;
 }
 static int do_new_game(tbx_pool *p, const uint8_t *mask, cudaStream_t s) {
   if (p->game == TBX_BREAKOUT) launch_new_game<TBX_BREAKOUT>(p, mask, s);
@@ -237,22 +244,30 @@ int tbx_new_game(tbx_pool *p, const uint8_t *mask, void *stream) {
   return do_new_game(p, mask, (cudaStream_t)stream);
 }
 
+struct SynStream { uint64_t seed, env0, t; };
 static int do_step(tbx_pool *p, const int32_t *actions, const uint8_t *inputs, int auto_reset, int32_t *reward, uint8_t *done,
-                   int32_t *score, int32_t *lives, cudaStream_t s) {
+                   int32_t *score, int32_t *lives, cudaStream_t s, const SynStream *syn = 0) {
   StepArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.actions = actions; a.inputs = inputs; a.auto_reset = auto_reset;
+  a.legal = p->d_legal; a.n_legal = p->info->n_legal;
+  a.syn_seed = syn ? syn->seed : 0; a.syn_env0 = syn ? syn->env0 : 0; a.syn_t = syn ? syn->t : 0;
   a.reward = reward; a.done = done; a.score = score; a.lives = lives; a.stats = p->d_stats; a.bad_actions = p->d_bad;
-  if (p->game == TBX_BREAKOUT) step_kernel<TBX_BREAKOUT><<<blocks(p->n, 128), 128, 0, s>>>(a);
-  else if (p->game == TBX_AMIDAR) step_kernel<TBX_AMIDAR><<<blocks(p->n, 128), 128, 0, s>>>(a);
-  else step_kernel<TBX_SPACE_INVADERS><<<blocks(p->n, 128), 128, 0, s>>>(a);
-  CK(cudaGetLastError());
-  return TBX_OK;
+  if (p->game == TBX_BREAKOUT) return launch_step<TBX_BREAKOUT>(p, a, s);
+  if (p->game == TBX_AMIDAR) return launch_step<TBX_AMIDAR>(p, a, s);
+  return launch_step<TBX_SPACE_INVADERS>(p, a, s);
 }
 int tbx_step(tbx_pool *p, const int32_t *actions, int auto_reset, int32_t *reward, uint8_t *done, int32_t *score, int32_t *lives, void *stream) {
   if (!p || !actions) return set_err(TBX_EINVAL, "pool/actions is NULL");
   CK(cudaSetDevice(p->device));
   return do_step(p, actions, 0, auto_reset, reward, done, score, lives, (cudaStream_t)stream);
+}
+int tbx_step_random(tbx_pool *p, uint64_t seed, uint64_t env0, uint64_t t, int auto_reset, int32_t *reward, uint8_t *done, int32_t *score, int32_t *lives,
+                    void *stream) {
+  if (!p) return set_err(TBX_EINVAL, "pool is NULL");
+  CK(cudaSetDevice(p->device));
+  SynStream syn = {seed, env0, t};
+  return do_step(p, 0, 0, auto_reset, reward, done, score, lives, (cudaStream_t)stream, &syn);
 }
 int tbx_step_inputs(tbx_pool *p, const uint8_t *inputs, int auto_reset, int32_t *reward, uint8_t *done, int32_t *score, int32_t *lives, void *stream) {
   if (!p || !inputs) return set_err(TBX_EINVAL, "pool/inputs is NULL");
@@ -277,7 +292,7 @@ int tbx_check(tbx_pool *p, void *stream) {
 /* ---- render */
 static void drop_render_cache(tbx_pool *p) {
   for (int b = 0; b < 2; b++) { cudaFree(p->d_base_gray[b]); cudaFree(p->d_base_rgba[b]); cudaFree(p->d_base_rgb[b]); p->d_base_gray[b] = p->d_base_rgba[b] = p->d_base_rgb[b] = 0; }
-  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); cudaFree(kv.second.d_patches[0]); cudaFree(kv.second.d_patches[1]); cudaFree(kv.second.d_direct); }
+  for (auto &kv : p->area) { cudaFree(kv.second.d_plan); cudaFree(kv.second.d_base_out[0]); cudaFree(kv.second.d_base_out[1]); cudaFree(kv.second.d_patches[0]); cudaFree(kv.second.d_patches[1]); cudaFree(kv.second.d_direct); cudaFree(kv.second.d_direct2); }
   p->area.clear();
 }
 /* base frames 0/1 of the current config (see tbx_render.cuh), gray and RGBA, on the device */
@@ -314,7 +329,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
     AreaRes r;
     r.plan = plan;
     r.dw = out_w; r.dh = out_h; r.tx = plan.tx; r.ty = plan.ty; r.d_plan = 0; r.d_base_out[0] = r.d_base_out[1] = 0; r.d_patches[0] = r.d_patches[1] = 0;
-    r.d_direct = 0; r.direct_ok = 0;
+    r.d_direct = r.d_direct2 = 0; r.direct_ok = 0;
     CK(cudaMalloc(&r.d_plan, sizeof plan));
     CK(cudaMemcpy(r.d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; b++) {
@@ -327,7 +342,7 @@ static int ensure_area(tbx_pool *p, int out_w, int out_h, AreaRes **out) {
       CK(cudaMalloc(&r.d_patches[b], patches.size() * sizeof(TbxDigitPatch)));
       CK(cudaMemcpy(r.d_patches[b], patches.data(), patches.size() * sizeof(TbxDigitPatch), cudaMemcpyHostToDevice));
     }
-    CK(tbx_direct_build(p->cfg, p->game == TBX_BREAKOUT ? &p->brk_tables[p->cfg.brk.default_tbl] : 0, rs, plan, p->h_base_gray[0].data(), &r.d_direct));
+    CK(tbx_direct_build(p->cfg, p->game == TBX_BREAKOUT ? &p->brk_tables[p->cfg.brk.default_tbl] : 0, rs, plan, p->h_base_gray[0].data(), &r.d_direct, &r.d_direct2));
     r.direct_ok = r.d_direct != 0;
     it = p->area.insert(std::make_pair(key, r)).first;
   }
@@ -422,7 +437,7 @@ template <int GAME> static int launch_render_mode(int mode, int tx, int ty, cons
 
 extern "C" {
 
-struct DualRender { const uint32_t *planes2; const uint8_t *reset_flags; int stack_k, stack_slot; };
+struct DualRender { const uint32_t *planes2; const uint8_t *reset_flags; int stack_k, stack_slot, stack_mode; };
 static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream, const DualRender *dual);
 
 int tbx_render(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h, void *stream) { return render_impl(p, dst, mode, out_w, out_h, stream, 0); }
@@ -442,7 +457,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
   RenderArgs a;
   a.planes = p->planes; a.n = p->n; a.n_pad = p->n_pad; a.cfg = p->d_cfg; a.tables = p->d_tables;
   a.planes2 = dual ? dual->planes2 : 0; a.reset_flags = dual ? dual->reset_flags : 0;
-  a.stack_k = dual ? dual->stack_k : 1; a.stack_slot = dual ? dual->stack_slot : 0; a.env_stride = fb * (size_t)a.stack_k; a.tile_bytes = 0;
+  a.stack_k = dual ? dual->stack_k : 1; a.stack_slot = dual ? dual->stack_slot : 0; a.stack_mode = dual ? dual->stack_mode : 0; a.env_stride = fb * (size_t)a.stack_k; a.tile_bytes = 0;
   a.patches[0] = a.patches[1] = 0; a.dense_list = 0; a.dense_count = 0; a.dense_flag = 0; a.dense_threshold = 0; a.env_list = 0; a.env_count = 0;
   a.dst = dst; a.frame_bytes = fb; a.plan = 0; a.out_h = out_h; a.tile_stride = 0; a.warp_bytes = 0; a.list_cap = 0; a.tile_hshift = 0; a.max_run = 0; a.band_rows = 0; a.smem_rects = 0;
   for (int b = 0; b < 2; b++) {
@@ -510,9 +525,10 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
         if (ar->direct_ok && !dual && !(ksel && !strcmp(ksel, "tile"))) {
           if (!p->d_fb) { CK(cudaMalloc(&p->d_fb, ((size_t)p->n_pad + 8) * sizeof(int32_t))); CK(cudaMemsetAsync(p->d_fb, 0, 8 * sizeof(int32_t), s)); }
           DirectArgs da;
-          da.aux = ar->d_direct; da.fb_list = p->d_fb + 8; da.fb_count = p->d_fb;
+          da.aux = ar->d_direct; da.aux2 = ar->d_direct2; da.fb_list = p->d_fb + 8; da.fb_count = p->d_fb;
           tbx_direct_geometry(p->game, out_w, out_h, da);
           CK(tbx_launch_direct(p->game, tx, ty, a, cfg_ptr(p), ar->plan, da, s));
+          if (p->game == TBX_SPACE_INVADERS) return TBX_OK; /* covers every env: nothing is handed over */
           a.env_list = p->d_fb + 8;
           a.env_count = p->d_fb;
         }
@@ -586,6 +602,8 @@ struct tbx_wrap {
   uint32_t *planes_prev, *wstate;
   uint8_t *was_reset;
   int head; /* ring slot of the newest frame */
+  int stack_mode; /* what a reset observation does to the other k-1 ring slots: 0 = fills them (FrameStack.reset), 1 = zeroes them (VecFrameStack) */
+  int32_t *ep_return, *ep_length; /* caller-owned device outputs of Monitor's episode record, or NULL */
 };
 
 extern "C" {
@@ -600,14 +618,14 @@ int tbx_wrap_create(tbx_pool *p, int skip, int noop_max, int episodic_life, int 
   tbx_wrap *w = new (std::nothrow) tbx_wrap();
   if (!w) return set_err(TBX_ENOMEM, "out of memory");
   w->pool = p; w->skip = skip; w->noop_max = noop_max; w->episodic_life = episodic_life; w->fire_reset = fire_reset; w->clip_rewards = clip_rewards;
-  w->stack_k = stack_k; w->out_w = out_w; w->out_h = out_h; w->noop_seed = noop_seed; w->env0 = env0; w->head = 0;
+  w->stack_k = stack_k; w->out_w = out_w; w->out_h = out_h; w->noop_seed = noop_seed; w->env0 = env0; w->head = 0; w->stack_mode = 0; w->ep_return = w->ep_length = 0;
   w->planes_prev = 0; w->wstate = 0; w->was_reset = 0;
   const size_t plane_bytes = (size_t)p->info->rec_words * p->n_pad * 4;
   cudaError_t e = cudaMalloc(&w->planes_prev, plane_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&w->wstate, 3 * (size_t)p->n_pad * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&w->wstate, 5 * (size_t)p->n_pad * 4);
   if (e == cudaSuccess) e = cudaMalloc(&w->was_reset, (size_t)p->n_pad);
   if (e == cudaSuccess) e = cudaMemcpy(w->planes_prev, p->planes, plane_bytes, cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess) e = cudaMemset(w->wstate, 0, 3 * (size_t)p->n_pad * 4);
+  if (e == cudaSuccess) e = cudaMemset(w->wstate, 0, 5 * (size_t)p->n_pad * 4);
   if (e == cudaSuccess) { /* EpisodicLifeEnv.__init__: lives = 0, was_real_done = True (atari_wrappers.py:155-156) */
     std::vector<uint32_t> ones((size_t)p->n_pad, 1u);
     e = cudaMemcpy(w->wstate + p->n_pad, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice);
@@ -619,6 +637,17 @@ int tbx_wrap_create(tbx_pool *p, int skip, int noop_max, int episodic_life, int 
     return set_err(TBX_ECUDA, std::string("tbx_wrap_create: ") + cudaGetErrorString(e));
   }
   *out = w;
+  return TBX_OK;
+}
+
+int tbx_wrap_set_stack_mode(tbx_wrap *w, int mode) {
+  if (!w || (mode != 0 && mode != 1)) return set_err(TBX_EINVAL, "wrap is NULL or unknown stack mode (0 = FrameStack, 1 = VecFrameStack)");
+  w->stack_mode = mode;
+  return TBX_OK;
+}
+int tbx_wrap_set_episode_outputs(tbx_wrap *w, int32_t *ep_return_dev, int32_t *ep_length_dev) {
+  if (!w) return set_err(TBX_EINVAL, "wrap is NULL");
+  w->ep_return = ep_return_dev; w->ep_length = ep_length_dev;
   return TBX_OK;
 }
 
@@ -643,6 +672,7 @@ int tbx_wrap_step(tbx_wrap *w, const int32_t *actions, uint8_t *obs_ring, int32_
   a.skip = w->skip; a.noop_max = w->noop_max; a.episodic_life = w->episodic_life; a.fire_reset = w->fire_reset; a.clip_rewards = w->clip_rewards;
   a.noop_seed = w->noop_seed; a.env0 = w->env0;
   a.reward = reward; a.score = score; a.lives = lives; a.done = done; a.real_done = real_done; a.was_reset = w->was_reset;
+  a.ep_return = w->ep_return; a.ep_length = w->ep_length;
   a.stats = p->d_stats; a.bad_actions = p->d_bad;
   if (p->game == TBX_BREAKOUT) wrap_step_kernel<TBX_BREAKOUT><<<blocks(p->n, 128), 128, 0, s>>>(a);
   else if (p->game == TBX_AMIDAR) wrap_step_kernel<TBX_AMIDAR><<<blocks(p->n, 128), 128, 0, s>>>(a);
@@ -651,7 +681,7 @@ int tbx_wrap_step(tbx_wrap *w, const int32_t *actions, uint8_t *obs_ring, int32_
   if (obs_ring) {
     w->head = (w->head + 1) % w->stack_k;
     DualRender d;
-    d.planes2 = w->planes_prev; d.reset_flags = w->was_reset; d.stack_k = w->stack_k; d.stack_slot = w->head;
+    d.planes2 = w->planes_prev; d.reset_flags = w->was_reset; d.stack_k = w->stack_k; d.stack_slot = w->head; d.stack_mode = w->stack_mode;
     int r = render_impl(p, obs_ring, TBX_OBS_GRAY_AREA, w->out_w, w->out_h, stream, &d);
     if (r) return r;
   }
@@ -694,6 +724,15 @@ int tbx_field_set(tbx_pool *p, const char *path, const void *values, const uint8
   const int also = (f.kind == TBX_F_I32 && f.word == TBX_FW(TbxHdr, score)) ? TBX_FW(TbxHdr, prev_score) : -1;
   field_set_kernel<<<blocks(p->n, 256), 256, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, f.word, f.kind, f.bit < 0 ? 0 : f.bit,
                                                                          (const int32_t *)values, (const double *)values, mask, also);
+  CK(cudaGetLastError());
+  return TBX_OK;
+}
+
+int tbx_breakout_columns(tbx_pool *p, int op, int col, const uint8_t *mask, int32_t *out, void *stream) {
+  if (!p || p->game != TBX_BREAKOUT) return set_err(TBX_EINVAL, "tbx_breakout_columns needs a breakout pool");
+  if (op < 0 || op > 2 || (op == 2 && !out)) return set_err(TBX_EINVAL, "op is 0 (remove column), 1 (fill column) or 2 (count channels into out)");
+  CK(cudaSetDevice(p->device));
+  brk_column_kernel<<<blocks(p->n, 128), 128, 0, (cudaStream_t)stream>>>(p->planes, p->n, p->n_pad, (const BrkTable *)p->d_tables, op, col, mask, out);
   CK(cudaGetLastError());
   return TBX_OK;
 }

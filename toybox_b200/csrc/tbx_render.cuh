@@ -134,6 +134,7 @@ struct RenderArgs {
   const uint8_t *reset_flags;
   size_t env_stride; /* bytes between the observations of consecutive envs (frame_bytes * stack_k) */
   int stack_k, stack_slot, tile_bytes;
+  int stack_mode; /* envs flagged in reset_flags: 0 = the frame goes into every slot (FrameStack.reset), 1 = the other slots are zeroed (VecFrameStack) */
   /* native layouts, broadcast + patch (tbx_render_native.cuh): envs with more than dense_threshold entries (by the
    * game's cheap estimate) are not patched but appended to dense_list; the canvas kernel then repaints exactly those
    * (env_list / env_count != NULL: CTA b renders envs env_list[8b .. 8b+7], b < ceil(*env_count / 8)) */

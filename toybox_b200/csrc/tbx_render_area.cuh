@@ -549,18 +549,20 @@ __global__ void __launch_bounds__(TBX_AREA_MAX_THREADS, TBX_AREA_MIN_CTAS) area_
         }
       }
     }
-    /* FrameStack.reset (atari_wrappers.py:262-266): a reset observation fills every slot of the env's ring */
+    /* a reset observation and the rest of the env's ring: FrameStack.reset (atari_wrappers.py:262-266) fills every slot with
+     * it; VecFrameStack (vec_env/vec_frame_stack.py:17-30) zeroes the stack and keeps the new frame only */
     if (a.reset_flags && a.stack_k > 1 && a.reset_flags[env]) {
       __syncwarp();
       uint8_t *ring = a.dst + (size_t)env * a.env_stride;
       const int nb = dw * dh;
+      const bool zero = a.stack_mode == 1;
       for (int k = 0; k < a.stack_k; k++) {
         if (k == a.stack_slot) continue;
         uint8_t *o2 = ring + (size_t)k * a.frame_bytes;
         if ((a.frame_bytes & 15) == 0) {
-          for (int i = lane; i < (nb >> 4); i += 32) reinterpret_cast<uint4 *>(o2)[i] = __ldcg(reinterpret_cast<const uint4 *>(out) + i);
+          for (int i = lane; i < (nb >> 4); i += 32) reinterpret_cast<uint4 *>(o2)[i] = zero ? make_uint4(0, 0, 0, 0) : __ldcg(reinterpret_cast<const uint4 *>(out) + i);
         } else {
-          for (int i = lane; i < nb; i += 32) o2[i] = __ldcg(out + i);
+          for (int i = lane; i < nb; i += 32) o2[i] = zero ? (uint8_t)0 : __ldcg(out + i);
         }
       }
     }

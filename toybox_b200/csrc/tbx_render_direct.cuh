@@ -302,5 +302,300 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
 #undef TBX_DIRECT_LAND
 }
 
+/* ------------------------------------------------------------------ Space Invaders: sparse sprites on a plain base
+ * (tbx_direct.h).  Same persistent-CTA frame as the Breakout kernel: the base down-sample in shared memory, one bulk copy
+ * of it per env, the records of a chunk staged word-major by cp.async (one stage: the next chunk is fetched as soon as
+ * every warp has taken its record).  Per env (warp):
+ *   1. the draw list's dynamic slots become ENTRIES in shared memory (clipped rectangle, gray, sprite reference, output
+ *      footprint), three passes of 32 slots, in draw order;
+ *   2. two bitmaps over the output pixels (covered once / covered twice) tell which entries share an output pixel with
+ *      another one; an entry that does not, lies on plain background and has a pre-resolved patch (bank sprite in a usual
+ *      colour, HUD digit) is a patch copy, one lane per entry;
+ *   3. the other entries' footprints form a pixel list shared out 32 at a time; each pixel's TX x TY source window is built
+ *      as packed bytes from base frame 0 and those entries in draw order (solid rectangles as byte masks, 16-bit sprites by
+ *      shifting the row's bits under the window) and resolved in cv2's tap order. */
+#define TBX_SI_DIRECT_MIN_CTAS 3
+#define TBX_E_SPRITE_PATCH 1u
+#define TBX_E_DIGIT_PATCH 2u
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ TbxAreaPlan plan_c,
+                                                                                            const __grid_constant__ DirectArgs d) {
+  constexpr int RW = TBX_WORDS(SiRec), W = TBX_SI_W, H = TBX_SI_H;
+  constexpr int RECW_BYTES = (RW * 4 + 15) & ~15;
+  extern __shared__ uint4 smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
+  uint8_t *sbase = smem;
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base); /* [RW][8 envs] */
+  const TbxSiDirect *__restrict__ Ap = reinterpret_cast<const TbxSiDirect *>(d.aux);
+  const TbxSiDirect &A = *Ap;
+  const TbxSpritePatch *__restrict__ spatch = reinterpret_cast<const TbxSpritePatch *>(d.aux2);
+  const TbxDigitPatch *__restrict__ dpatch = a.patches[0];
+  const TbxAreaPlan *__restrict__ plan = a.plan;
+  const TbxAreaPlan &cp = plan_c;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int dw = cp.dw, dh = cp.dh, nb = dw * dh, ow = (dw + 31) >> 5; /* ow: bitmap words per output row */
+  uint8_t *wmem = smem + d.smem_base + RW * TBX_EPC * 4 + wid * d.warp_bytes;
+  uint32_t *recw = reinterpret_cast<uint32_t *>(wmem);
+  int4 *ent = reinterpret_cast<int4 *>(wmem + RECW_BYTES);                       /* 2 x int4 per entry */
+  uint32_t *occ1 = reinterpret_cast<uint32_t *>(ent + 2 * TBX_SD_MAX_ENTRIES);   /* [dh][ow]: covered by an entry */
+  uint32_t *occ2 = occ1 + dh * ow;                                               /* covered by two or more */
+  int *lst = reinterpret_cast<int *>(occ2 + dh * ow);                            /* evaluated entries: id, then pixel count */
+  int *lcnt = lst + TBX_SD_MAX_ENTRIES;
+  const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
+  const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
+  const int n_sets = A.n_sets, pxp = A.px_period, pyp = A.py_period;
+  const uint32_t inv_px = A.inv_px, inv_py = A.inv_py;
+  const uint32_t *__restrict__ base0w = reinterpret_cast<const uint32_t *>(a.base[0]);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  auto prefetch = [&](int chunk) {
+    const uint32_t *src = a.planes + (size_t)chunk * TBX_EPC;
+    for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(stage + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x);
+  for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[0]) + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t *R = recw;
+
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads(); /* the chunk's records have landed; every warp is done with its previous env */
+    const int env = chunk * TBX_EPC + wid;
+    if (env < a.n)
+      for (int w = lane; w < RW; w += 32) recw[w] = stage[w * TBX_EPC + wid];
+    __syncthreads(); /* the stage is free again */
+    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x);
+    if (env >= a.n) continue;
+    uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
+    if (bulk) {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"((uint32_t)__cvta_generic_to_shared(sbase)), "r"((uint32_t)nb) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int i = lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(sbase)[i];
+    }
+    /* 1. entries */
+    for (int i = lane; i < 2 * dh * ow; i += 32) occ1[i] = 0;
+    int n = 0;
+    for (int s0 = SI_N_STATIC; s0 < SI_N_SLOTS; s0 += 32) {
+      const int slot = s0 + lane;
+      TbxPrim p = tbx_prim_none();
+      if (slot < SI_N_SLOTS) p = si_prim(R, slot);
+      const int x0 = max((int)p.x, 0), y0 = max((int)p.y, 0), x1 = min((int)p.x + (int)p.w, W), y1 = min((int)p.y + (int)p.h, H);
+      const bool ok = p.h > 0 && x0 < x1 && y0 < y1;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int fx0 = __ldg(&plan->xdlo[x0]), fx1 = __ldg(&plan->xdhi[x1 - 1]), fy0 = __ldg(&plan->ydlo[y0]), fy1 = __ldg(&plan->ydhi[y1 - 1]);
+        const uint32_t gray = tbx_luma(p.color);
+        uint32_t kind = 0, ref = 0;
+        const bool whole = p.x >= 0 && p.y >= 0 && (int)p.x + (int)p.w <= W && (int)p.y + (int)p.h <= H;
+        if (whole && p.bw == 3 && slot < SI_SLOT_SHIELDS && p.off < TBX_BANK_FONT + 50 && dpatch) { /* a HUD digit */
+          ref = (uint32_t)(slot - SI_SLOT_SCORE) * 10u + p.off / 5u;
+          if (__ldg(&dpatch[ref].w) != 0) kind = TBX_E_DIGIT_PATCH;
+        } else if (whole && n_sets && p.bw == 16 && p.scale == 0x11 && !(p.off & TBX_PRIM_STATE) && p.off >= TBX_BANK_INVADER) { /* a bank sprite: is there a patch set for (sprite, gray)? */
+          const int idx = p.off >= TBX_BANK_BOOM ? 8 + ((int)p.off - TBX_BANK_BOOM) / 10 : ((int)p.off - TBX_BANK_INVADER) / 10;
+          const uint32_t cand = __ldg(reinterpret_cast<const uint32_t *>(A.set_lut[idx & 15]));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t s = (cand >> (8 * k)) & 255u;
+            if (s != 255u && __ldg(&A.set_off[s]) == p.off && __ldg(&A.set_gray[s]) == gray && (int)__ldg(&A.set_h[s]) == (int)p.h) { kind = TBX_E_SPRITE_PATCH; ref = s; }
+          }
+        }
+        const int e = n + __popc(m & lt_mask);
+        ent[2 * e] = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), (int)((uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16)), (int)(gray | (kind << 8) | (ref << 16)));
+        ent[2 * e + 1] = make_int4((int)((uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24)), fx0 | (fx1 << 8) | (fy0 << 16) | (fy1 << 24), 0, 0);
+      }
+      n += __popc(m);
+    }
+    __syncwarp();
+    /* 2. which entries share an output pixel with another one */
+    for (int e = lane; e < n; e += 32) {
+      const uint32_t fp = (uint32_t)ent[2 * e + 1].y;
+      const int fx0 = fp & 255u, fx1 = (fp >> 8) & 255u, fy0 = (fp >> 16) & 255u, fy1 = fp >> 24;
+      for (int w = fx0 >> 5; w <= fx1 >> 5; w++) {
+        const uint32_t mask = (w == fx0 >> 5 ? 0xffffffffu << (fx0 & 31) : 0xffffffffu) & (w == fx1 >> 5 ? 0xffffffffu >> (31 - (fx1 & 31)) : 0xffffffffu);
+        for (int r = fy0; r <= fy1; r++) {
+          const uint32_t dup = atomicOr(&occ1[r * ow + w], mask) & mask;
+          if (dup) atomicOr(&occ2[r * ow + w], dup);
+        }
+      }
+    }
+    __syncwarp();
+    int n_eval = 0, total = 0;
+    bool any_shared = false;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      bool patch = false, shared = false;
+      int area = 0;
+      if (e < n) {
+        const uint32_t fp = (uint32_t)ent[2 * e + 1].y;
+        const int fx0 = fp & 255u, fx1 = (fp >> 8) & 255u, fy0 = (fp >> 16) & 255u, fy1 = fp >> 24;
+        area = (fx1 - fx0 + 1) * (fy1 - fy0 + 1);
+        const uint32_t kind = ((uint32_t)ent[2 * e].w >> 8) & 255u;
+        bool plain = true; /* sprite patches assume background around them; digit patches were resolved on the base itself */
+        for (int w = fx0 >> 5; w <= fx1 >> 5 && !shared; w++) {
+          const uint32_t mask = (w == fx0 >> 5 ? 0xffffffffu << (fx0 & 31) : 0xffffffffu) & (w == fx1 >> 5 ? 0xffffffffu >> (31 - (fx1 & 31)) : 0xffffffffu);
+          for (int r = fy0; r <= fy1; r++) {
+            if (occ2[r * ow + w] & mask) { shared = true; break; }
+            if (kind == TBX_E_SPRITE_PATCH && (__ldg(&A.plain[r][w]) & mask) != mask) plain = false;
+          }
+        }
+        patch = kind != 0 && !shared && plain;
+        if (patch) ent[2 * e + 1].z = 1; /* rendered as a patch below */
+      }
+      const unsigned em = __ballot_sync(0xffffffffu, e < n && !patch);
+      if (e < n && !patch) { const int k = n_eval + __popc(em & lt_mask); lst[k] = e | (shared ? 0x10000 : 0); lcnt[k] = area; }
+      n_eval += __popc(em);
+      total += __reduce_add_sync(0xffffffffu, (e < n && !patch) ? area : 0);
+      any_shared |= __any_sync(0xffffffffu, shared);
+    }
+    /* the base copy must have landed before anything is written over it */
+    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+    /* 2b. patches: one lane per entry */
+    for (int e = lane; e < n; e += 32) {
+      const int4 e1 = ent[2 * e + 1];
+      if (!e1.z) continue;
+      const int4 e0 = ent[2 * e];
+      const uint32_t meta = (uint32_t)e0.w, kind = (meta >> 8) & 255u, ref = meta >> 16;
+      const uint32_t fp = (uint32_t)e1.y;
+      const int fx0 = fp & 255u, fy0 = (fp >> 16) & 255u;
+      uint8_t *o = out + fy0 * dw + fx0;
+      if (kind == TBX_E_SPRITE_PATCH) {
+        const uint32_t ox = (uint32_t)(uint16_t)e0.z, oy = (uint32_t)e0.z >> 16; /* whole sprites: non-negative origin */
+        const uint32_t xph = inv_px ? ox - __umulhi(ox, inv_px) * (uint32_t)pxp : 0u, yph = inv_py ? oy - __umulhi(oy, inv_py) * (uint32_t)pyp : 0u;
+        const uint4 *P = reinterpret_cast<const uint4 *>(spatch + ((size_t)ref * pyp + yph) * pxp + xph);
+        const uint4 q0 = __ldg(P), q1 = __ldg(P + 1);
+        const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const int pw = qw[0] & 255u, ph = (qw[0] >> 8) & 255u;
+#pragma unroll
+        for (int r = 0; r < TBX_SP_MAX_H; r++)
+#pragma unroll
+          for (int c = 0; c < TBX_SP_MAX_W; c++) {
+            const int b = 2 + r * TBX_SP_MAX_W + c;
+            if (r < ph && c < pw) o[r * dw + c] = (uint8_t)(qw[b >> 2] >> (8 * (b & 3)));
+          }
+      } else {
+        const TbxDigitPatch *P = dpatch + ref;
+        const int pw = __ldg(&P->w), ph = __ldg(&P->h);
+        for (int r = 0; r < ph; r++)
+          for (int c = 0; c < pw; c++) o[r * dw + c] = __ldg(&P->px[r * pw + c]);
+      }
+    }
+    /* 3. the evaluated entries' pixels.  A pixel of an entry that shares no output pixel with another one sees that entry
+     * only; pixels of entries that do are painted with every such entry, in draw order. */
+    __syncwarp();
+    for (int p0 = 0; p0 < total; p0 += 32) {
+      const int l = p0 + lane;
+      int myk = 0, myi = 0, off = 0;
+      for (int k = 0; k < n_eval; k++) {
+        const int cnt = lcnt[k];
+        if (l >= off && l < off + cnt) { myk = k; myi = l - off; }
+        off += cnt;
+      }
+      const bool act = l < total;
+      const int mine = lst[myk];
+      const bool conf = (mine >> 16) != 0;
+      const uint32_t fp = (uint32_t)ent[2 * (mine & 0xffff) + 1].y;
+      const int fx0 = fp & 255u, fx1 = (fp >> 8) & 255u, fy0 = (fp >> 16) & 255u;
+      const int ncol = fx1 - fx0 + 1;
+      const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, __ldg(&A.inv32[ncol])) : myi;
+      const int dx = act ? fx0 + myi - q * ncol : 0, dy = act ? fy0 + q : 0;
+      const int xs = __ldg(&plan->xs0[dx]), ys = __ldg(&plan->ys0[dy]);
+      uint32_t lo[TY], hi[TY];
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        const int y = min(ys + k, H - 1);
+        const int ob = y * W + xs;
+        const uint32_t w0 = __ldg(base0w + (ob >> 2)), w1 = __ldg(base0w + (ob >> 2) + 1);
+        lo[k] = __funnelshift_r(w0, w1, 8 * (ob & 3));
+        hi[k] = 0;
+        if (TX > 4) { const uint32_t w2 = __ldg(base0w + (ob >> 2) + 2); hi[k] = __funnelshift_r(w1, w2, 8 * (ob & 3)) & 255u; }
+      }
+      /* paint entry `id` into this lane's window */
+      auto paint = [&](int id) {
+        const int4 e0 = ent[2 * id];
+        const int x0 = e0.x & 0xffff, y0 = (uint32_t)e0.x >> 16, x1 = e0.y & 0xffff, y1 = (uint32_t)e0.y >> 16;
+        const int ta = max(x0 - xs, 0), tb = min(x1 - xs, TX), ka = max(y0 - ys, 0), kb = min(y1 - ys, TY);
+        if (ta >= tb || ka >= kb) return;
+        const uint32_t spr = (uint32_t)ent[2 * id + 1].x;
+        const uint32_t g = (uint32_t)e0.w & 255u, g4 = g * 0x01010101u;
+        const int bw = (spr >> 16) & 255u;
+        if (bw == 0) { /* a solid rectangle */
+          const uint32_t below_b = tb >= 4 ? 0xffffffffu : (1u << (8 * tb)) - 1u, below_a = ta >= 4 ? 0xffffffffu : (1u << (8 * ta)) - 1u;
+          const uint32_t bm = below_b & ~below_a;
+          const bool h5 = TX > 4 && ta <= 4 && tb > 4;
+#pragma unroll
+          for (int k = 0; k < TY; k++)
+            if (k >= ka && k < kb) { lo[k] = (lo[k] & ~bm) | (g4 & bm); if (h5) hi[k] = g; }
+          return;
+        }
+        const int ox = (int16_t)(e0.z & 0xffff), oy = (int16_t)((uint32_t)e0.z >> 16);
+        const uint32_t o = spr & 0xffffu;
+        const bool in_state = (o & TBX_PRIM_STATE) != 0;
+        const int ro = in_state ? (int)(o & 0x7fffu) : (int)o;
+        const int sc = spr >> 24, sx = sc & 15, sy = sc >> 4;
+        if (bw == 16 && sc == 0x11) { /* 16 pixels per row at scale 1: shift the row's bits under the window */
+          const int dd = xs - ox;
+#pragma unroll
+          for (int k = 0; k < TY; k++)
+            if (k >= ka && k < kb) {
+              const int ry = ys + k - oy;
+              const uint32_t bits = in_state ? R[ro + ry] : __ldg(&d_bank[ro + ry]);
+              const uint32_t rev = __brev(bits << 16); /* pixel q of the row at bit q */
+              const uint32_t m5 = (dd >= 0 ? rev >> dd : rev << (-dd)) & 31u;
+              const uint32_t bm = (((m5 & 15u) * 0x00204081u) & 0x01010101u) * 255u;
+              lo[k] = (lo[k] & ~bm) | (g4 & bm);
+              if (TX > 4 && (m5 & 16u)) hi[k] = g;
+            }
+          return;
+        }
+        /* any other sprite (zoomed HUD digits that touch something): tap by tap */
+        const uint32_t ix = d_inv16[sx], iy = d_inv16[sy];
+        for (int k = ka; k < kb; k++) {
+          const int py = ys + k - oy;
+          const int sy_i = sy == 1 ? py : (int)(((uint32_t)py * iy) >> 16);
+          const uint32_t bits = in_state ? R[ro + sy_i] : __ldg(&d_bank[ro + sy_i]);
+          uint32_t bm = 0;
+          bool b5 = false;
+          for (int t = ta; t < tb; t++) {
+            const int px = xs + t - ox;
+            const int sx_i = sx == 1 ? px : (int)(((uint32_t)px * ix) >> 16);
+            if ((bits >> (bw - 1 - sx_i)) & 1u) { if (t < 4) bm |= 255u << (8 * t); else b5 = true; }
+          }
+#pragma unroll
+          for (int kk = 0; kk < TY; kk++)
+            if (kk == k) { lo[kk] = (lo[kk] & ~bm) | (g4 & bm); if (b5) hi[kk] = g; }
+        }
+      };
+      if (act && !conf) paint(mine & 0xffff);
+      if (any_shared && __any_sync(0xffffffffu, act && conf)) {
+        for (int k2 = 0; k2 < n_eval; k2++) { /* draw order */
+          const int id = lst[k2];
+          if (!(id >> 16)) continue;
+          if (act && conf) paint(id & 0xffff);
+        }
+      }
+      float al[TX];
+#pragma unroll
+      for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        float h = tbx_fmul(tbx_u8f(lo[k] & 255u), al[0]);
+#pragma unroll
+        for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(t < 4 ? (lo[k] >> (8 * t)) & 255u : hi[k]), al[t]));
+        const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+        acc = k == 0 ? bh : tbx_fadd(acc, bh);
+      }
+      const int iv = tbx_f2i_rn_small(acc);
+      if (act) out[dy * dw + dx] = (uint8_t)(iv > 255 ? 255 : iv);
+    }
+  }
+}
+
 } /* namespace tbxk */
 #endif

@@ -105,24 +105,27 @@ def breakout_fill_column(pool, col, mask=None):
 
 
 def _breakout_set_column(pool, col, alive, mask):
-    cfg = pool.config_to_json()
-    n_rows = len(cfg["row_colors"]) if "row_colors" in cfg else 6
-    for r in range(n_rows):
-        pool.set_property("bricks[%d].alive" % (col * n_rows + r), alive, mask)
+    """one launch over the alive-mask words (tbx_breakout_columns); columns are the bricks' own `col` field, so envs whose brick
+    tables were edited through JSON are handled like query_state_json('count_channels') handles them"""
+    import torch
+    from . import _lib
+    from .pool import _ptr, _stream
+    m = None
+    if mask is not None:
+        m = torch.as_tensor(mask, device=pool.device).to(torch.uint8).contiguous()
+        if m.numel() != pool.n_envs:
+            raise ValueError("expected a mask of %d entries" % pool.n_envs)
+    _lib.check(pool.L.tbx_breakout_columns(pool._h, 1 if alive else 0, int(col), _ptr(m), None, _stream(pool.device)))
 
 
 def breakout_channel_count(pool):
-    """channels per env (column with every brick dead), as ctoybox's breakout_channel_count query: int32[N]"""
+    """channels per env (columns with every brick dead), as ctoybox's breakout_channel_count query: int32[N], one launch"""
     import torch
-    cfg = pool.config_to_json()
-    n_rows = len(cfg["row_colors"]) if "row_colors" in cfg else 6
-    total = torch.zeros(pool.n_envs, dtype=torch.int32, device=pool.device)
-    for c in range(18):
-        alive = torch.zeros(pool.n_envs, dtype=torch.bool, device=pool.device)
-        for r in range(n_rows):
-            alive |= pool.get_property("bricks[%d].alive" % (c * n_rows + r))
-        total += (~alive).int()
-    return total
+    from . import _lib
+    from .pool import _ptr, _stream
+    out = torch.empty(pool.n_envs, dtype=torch.int32, device=pool.device)
+    _lib.check(pool.L.tbx_breakout_columns(pool._h, 2, 0, None, _ptr(out), _stream(pool.device)))
+    return out
 
 
 def amidar_set_mode(pool, mode, time=None, mask=None):

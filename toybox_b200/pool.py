@@ -141,6 +141,12 @@ class BatchedToybox:
         _lib.check(self.L.tbx_step_inputs(self._h, _ptr(a), int(auto_reset), _ptr(self.reward), _ptr(self.done), _ptr(self.score),
                                           _ptr(self.lives), _stream(self.device)))
 
+    def step_random(self, seed, t, env0=0, auto_reset=True):
+        """apply_ale_action with the benchmark's reproducible uniform-over-legal action stream generated inside the step
+        kernel (one launch; same states as fill_random_actions + apply_ale_action)."""
+        _lib.check(self.L.tbx_step_random(self._h, int(seed), int(env0), int(t), int(auto_reset), _ptr(self.reward), _ptr(self.done),
+                                          _ptr(self.score), _ptr(self.lives), _stream(self.device)))
+
     def check(self):
         """Synchronise and raise ValueError if any env was handed an invalid ALE action id."""
         _lib.check(self.L.tbx_check(self._h, _stream(self.device)))
@@ -284,20 +290,31 @@ class BatchedToybox:
         _lib.check(self.L.tbx_field_set(self._h, path.encode(), _ptr(v), _ptr(m), _stream(self.device)))
 
     # ------------------------------------------------------------------ JSON (interventions)
-    def to_state_json(self, env_ids=None):
+    def to_state_json_text(self, env_ids=None):
+        """Toybox.to_state_json() of the listed envs as JSON TEXT (bytes), one document per env: the batched export without
+        the Python object trees (decode only the documents you edit)."""
         ids = np.arange(self.n_envs, dtype=np.int32) if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         out = (C.c_void_p * len(ids))()
         torch.cuda.synchronize(self.device)
         _lib.check(self.L.tbx_state_to_json(self._h, ids.ctypes.data_as(C.c_void_p), len(ids), out))
-        return [json.loads(_lib.take_str(p)) for p in out]
+        docs = []
+        for p in out:
+            docs.append(C.string_at(p))
+            self.L.tbx_free_str(p)
+        return docs
+
+    def to_state_json(self, env_ids=None):
+        return [json.loads(d) for d in self.to_state_json_text(env_ids)]
 
     state_to_json = to_state_json
 
     def write_state_json(self, states, env_ids=None):
+        """Toybox.write_state_json for the listed envs; `states` holds dicts or JSON text (str / bytes), one per env."""
         ids = np.arange(self.n_envs, dtype=np.int32) if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         if len(states) != len(ids):
             raise ValueError("one state per env id expected")
-        arr = (C.c_char_p * len(ids))(*[json.dumps(s).encode() for s in states])
+        docs = [s if isinstance(s, bytes) else s.encode() if isinstance(s, str) else json.dumps(s).encode() for s in states]
+        arr = (C.c_char_p * len(ids))(*docs)
         torch.cuda.synchronize(self.device)
         _lib.check(self.L.tbx_state_from_json(self._h, ids.ctypes.data_as(C.c_void_p), len(ids), arr))
 

@@ -10,6 +10,8 @@ observation_space, action_space; auto-reset and `infos[i]['episode']` as vec_env
 bench/monitor.py:58-76 provide them).
 """
 import ctypes as C
+import json
+import os
 import time
 
 import numpy as np
@@ -30,7 +32,12 @@ class DeepmindToybox:
     A finished env is reset inside the same call and `obs` then holds its reset observation (VecEnv semantics)."""
 
     def __init__(self, game, n_envs, device=None, seeds=None, config=None, frame_skip=4, noop_max=30, episode_life=True,
-                 fire_reset=True, clip_rewards=True, frame_stack=4, size=(84, 84), noop_seed=0, env0=0):
+                 fire_reset=True, clip_rewards=True, frame_stack=4, size=(84, 84), noop_seed=0, env0=0, stack_reset="fill"):
+        """stack_reset: what a reset observation does to the other k-1 ring slots -- "fill" (FrameStack.reset,
+        atari_wrappers.py:262-266: wrap_deepmind(frame_stack=True), the deepq path) or "zero" (VecFrameStack,
+        vec_env/vec_frame_stack.py:17-30: make_vec_env + VecFrameStack, the ppo2 / a2c path of run.py:123-125)."""
+        if stack_reset not in ("fill", "zero"):
+            raise ValueError("stack_reset is 'fill' (FrameStack) or 'zero' (VecFrameStack)")
         self.pool = BatchedToybox(game, n_envs, device=device, obs=("gray_area", size[0], size[1]), config=config, seeds=seeds)
         self.L = self.pool.L
         self.n_envs, self.device = self.pool.n_envs, self.pool.device
@@ -39,7 +46,12 @@ class DeepmindToybox:
         _lib.check(self.L.tbx_wrap_create(self.pool._h, int(frame_skip), int(noop_max), int(bool(episode_life)), int(bool(fire_reset)),
                                           int(bool(clip_rewards)), self.k, self.out_w, self.out_h, int(noop_seed), int(env0), C.byref(h)))
         self._w = h
+        _lib.check(self.L.tbx_wrap_set_stack_mode(self._w, 1 if stack_reset == "zero" else 0))
         n, dev = self.n_envs, self.device
+        # Monitor's episode record (bench/monitor.py:58-76) of the episode that ended in the last agent step, where real_done
+        self.ep_return = torch.zeros(n_envs, dtype=torch.int32, device=self.device)
+        self.ep_length = torch.zeros(n_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self.L.tbx_wrap_set_episode_outputs(self._w, _ptr(self.ep_return), _ptr(self.ep_length)))
         self.obs = torch.zeros((n, self.k, self.out_h, self.out_w), dtype=torch.uint8, device=dev)
         self.reward = torch.zeros(n, dtype=torch.int32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -80,7 +92,8 @@ class DeepmindToybox:
             if actions.numel() != self.n_envs:
                 raise ValueError("expected %d actions" % self.n_envs)
         self._call(actions, render)
-        return self.obs, self.reward, self.done, {"lives": self.lives, "score": self.score, "real_done": self.real_done}
+        return self.obs, self.reward, self.done, {"lives": self.lives, "score": self.score, "real_done": self.real_done,
+                                                    "ep_return": self.ep_return, "ep_length": self.ep_length}
 
     def check(self):
         self.pool.check()
@@ -107,10 +120,16 @@ class _Discrete:
 
 class ToyboxVecEnv:
     """The VecEnv surface of baselines (vec_env/__init__.py:26-131) over a DeepmindToybox: numpy in, numpy out, one
-    process, one GPU; `infos[i]['episode'] = {'r', 'l', 't'}` when env i's game ends, as Monitor reports it
-    (bench/monitor.py:58-76: r = sum of raw rewards, l = agent steps, t = seconds since start)."""
+    process, one GPU.  It stands for `VecFrameStack(make_vec_env(env_id, 'atari', n, seed), 4)` (run.py:123-125): the stack
+    of a finished env is zeroed and holds its reset observation only (vec_frame_stack.py:17-30), and
+    `infos[i]['episode'] = {'r', 'l', 't'}` appears when env i's game ends, exactly as the Monitor between make_atari and
+    wrap_deepmind reports it (bench/monitor.py:58-76: r = sum of raw rewards, l = MaxAndSkipEnv steps incl. those of
+    FireResetEnv / EpisodicLifeEnv resets, t = seconds since start) -- both counters are kept by the step kernel.
+    monitor_file: path of a Monitor-compatible CSV (bench/monitor.py:22-28,70-71,96-126: a '#{json header}' line, then the
+    columns r,l,t), one row per finished episode."""
 
-    def __init__(self, game, num_envs, **kw):
+    def __init__(self, game, num_envs, monitor_file=None, **kw):
+        kw.setdefault("stack_reset", "zero")
         self.env = DeepmindToybox(game, num_envs, **kw)
         self.num_envs = int(num_envs)
         e = self.env
@@ -118,16 +137,19 @@ class ToyboxVecEnv:
         self.action_space = _Discrete(e.n_actions)
         self._actions = None
         self._t0 = time.time()
-        self._ep_len = np.zeros(self.num_envs, np.int64)
-        self._ep_ret = np.zeros(self.num_envs, np.int64)
-        self._last_score = np.zeros(self.num_envs, np.int64)
         self.closed = False
+        self.episode_rewards, self.episode_lengths, self.episode_times = [], [], []
+        self._csv = None
+        if monitor_file is not None:
+            if not monitor_file.endswith("monitor.csv"):
+                monitor_file = monitor_file + ".monitor.csv" if not os.path.isdir(monitor_file) else os.path.join(monitor_file, "monitor.csv")
+            self._csv = open(monitor_file, "wt")
+            self._csv.write("#%s\n" % json.dumps({"t_start": self._t0, "env_id": "%sToyboxNoFrameskip-v4" % game.title().replace("_", "")}))
+            self._csv.write("r,l,t\n")
+            self._csv.flush()
 
     def reset(self):
         self.env.reset()
-        self._ep_len[:] = 0
-        self._ep_ret[:] = 0
-        self._last_score[:] = self.env.pool.get_score().cpu().numpy()
         return self.env.stacked().cpu().numpy()
 
     def step_async(self, actions):
@@ -135,7 +157,6 @@ class ToyboxVecEnv:
 
     def step_wait(self):
         e = self.env
-        # raw (unclipped) reward of the agent step for the Monitor-style episode record: score deltas of the game
         e.step(self._actions)
         obs = e.stacked().cpu().numpy()
         rew = e.reward.cpu().numpy().astype(np.float32)
@@ -143,18 +164,20 @@ class ToyboxVecEnv:
         real = e.real_done.cpu().numpy().astype(bool)
         score = e.score.cpu().numpy().astype(np.int64)
         lives = e.lives.cpu().numpy()
-        self._ep_len += 1
-        self._ep_ret += np.maximum(score - self._last_score, 0)
-        self._last_score = score
-        infos = []
-        for i in range(self.num_envs):
-            info = {"lives": int(lives[i]), "score": 0 if real[i] else int(score[i])}
-            if real[i]:
-                info["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
-                self._ep_len[i] = 0
-                self._ep_ret[i] = 0
-                self._last_score[i] = 0
-            infos.append(info)
+        infos = [{"lives": int(lives[i]), "score": int(score[i])} for i in range(self.num_envs)]
+        if real.any():
+            ep_r, ep_l = e.ep_return.cpu().numpy(), e.ep_length.cpu().numpy()
+            t = round(time.time() - self._t0, 6)
+            for i in np.flatnonzero(real):
+                ep = {"r": round(float(ep_r[i]), 6), "l": int(ep_l[i]), "t": t}
+                infos[i]["episode"] = ep
+                self.episode_rewards.append(ep["r"])
+                self.episode_lengths.append(ep["l"])
+                self.episode_times.append(t)
+                if self._csv is not None:
+                    self._csv.write("%s,%d,%s\n" % (ep["r"], ep["l"], ep["t"]))
+            if self._csv is not None:
+                self._csv.flush()
         return obs, rew, done, infos
 
     def step(self, actions):
@@ -165,6 +188,17 @@ class ToyboxVecEnv:
         if not self.closed:
             self.env.close()
             self.closed = True
+            if self._csv is not None:
+                self._csv.close()
+
+    def get_episode_rewards(self):           # the Monitor accessors of bench/monitor.py:84-94
+        return self.episode_rewards
+
+    def get_episode_lengths(self):
+        return self.episode_lengths
+
+    def get_episode_times(self):
+        return self.episode_times
 
     def get_images(self):
         return self.env.pool.render(obs="rgb").cpu().numpy()
