@@ -636,6 +636,49 @@ def main():
                "pcie_note": "pcie_gbs = a bare pinned cudaMemcpyAsync D2H of the observation bytes per rank, all %d rank(s) copying at the "
                             "same time: the host-side ceiling of this call" % world}
         del h_obs
+        # the call a trainer makes: the wrapped env (frame skip 4 + max of 2 + 84x84 + 4-frame stack), host actions in, the observation
+        # stack + reward + done out to pinned host memory -- one observation per 4 game frames
+        if args.game == "breakout" and args.obs == "gray84":
+            from toybox_b200.wrappers import DeepmindToybox
+            wenv = DeepmindToybox(args.game, n, device=dev, seeds=(1234 + rank * n + np.arange(n, dtype=np.int64)) & 0xFFFFFFFF, env0=rank * n, stack_reset="zero")
+            wenv.reset()
+            hw_act = torch.from_numpy(rng.integers(0, wenv.n_actions, size=n).astype(np.int32)).pin_memory()
+            d_act = torch.empty(n, dtype=torch.int32, device=dev)
+            hw_obs = torch.empty((n, wenv.k, wenv.out_h, wenv.out_w), dtype=torch.uint8).pin_memory()
+            hw_new = torch.empty((n, wenv.out_h, wenv.out_w), dtype=torch.uint8).pin_memory()
+            d_new = torch.empty((n, wenv.out_h, wenv.out_w), dtype=torch.uint8, device=dev)
+            hw_rew = torch.empty(n, dtype=torch.int32).pin_memory()
+            hw_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+            def wstep(full):
+                d_act.copy_(hw_act, non_blocking=True)
+                wenv.step(d_act)
+                if full:
+                    hw_obs.copy_(wenv.obs, non_blocking=True)
+                else:                   # the newest observation only (the host keeps the stack): gathered on the device, one contiguous copy
+                    d_new.copy_(wenv.obs[:, wenv.slot])
+                    hw_new.copy_(d_new, non_blocking=True)
+                hw_rew.copy_(wenv.reward, non_blocking=True)
+                hw_done.copy_(wenv.done, non_blocking=True)
+                torch.cuda.synchronize(dev)
+
+            wrapped = {}
+            for name, full in (("stack_of_4", True), ("newest_frame", False)):
+                for _ in range(3):
+                    wstep(full)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(ke):
+                    wstep(full)
+                barrier()
+                wsec = max_over_ranks(time.perf_counter() - t0)
+                wb = n * (fb * (wenv.k if full else 1) + 4 + 1)
+                wrapped[name] = {"agent_steps_per_sec": world * n * ke / wsec, "game_frames_per_sec": 4 * world * n * ke / wsec, "d2h_bytes_per_step": wb,
+                                 "achieved_gbs": wb * ke / wsec / 1e9, "frac_of_pcie": (wb * ke / wsec / 1e9) / pcie}
+            e2e["wrapped"] = wrapped
+            e2e["wrapped_api"] = "DeepmindToybox.step (tbx_wrap_step): pinned host actions in; observation ring (or its newest slot), reward, done out to pinned host memory"
+            wenv.close()
+            del hw_obs, hw_new
 
     # ---- the same pool from other game states, as named sub-records (the render cost follows what differs from a fresh game)
     states = {}

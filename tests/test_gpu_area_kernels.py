@@ -230,18 +230,28 @@ def test_si_direct_kernel_adversarial_states(tbx, oracle_mod):
                     got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
                     bad = np.argwhere(got != want)
                     assert bad.size == 0, (rnd, ow, oh, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+            for mode in ("rgb", "gray", "rgba"):              # native layouts: broadcast + patch / canvas kernel
+                want = ref.render(mode).reshape(n, -1)
+                for v in ({}, {"TBX_NATIVE_KERNEL": "canvas"}):
+                    for k in ("TBX_NATIVE_KERNEL",):
+                        os.environ.pop(k, None)
+                    os.environ.update(v)
+                    got = pool.render(obs=mode).cpu().numpy().reshape(n, -1)
+                    bad = np.argwhere(got != want)
+                    assert bad.size == 0, (rnd, mode, v, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
             for t in range(30):
                 acts = legal[[oracle_mod.action_index(0xB200, i, 500 + t, len(legal)) for i in range(n)]]
                 pool.apply_ale_action(acts, auto_reset=True)
                 ref.step(acts, auto_reset=True)
     finally:
+        os.environ.pop("TBX_NATIVE_KERNEL", None)
         _set_env({})
         pool.close()
 
 
 def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
-    """late-game Amidar boards (long painted corridors, painted boxes): runs of equal tiles are merged into one entry;
-    every layout and renderer against the oracle"""
+    """late-game Amidar boards (long painted corridors, painted boxes, moved / removed / caught enemies, off-board player): the
+    direct kernel's tile-look grid and the tile kernel's merged runs; every layout and renderer against the oracle"""
     n = 24
     pool, ref = _advance(tbx, oracle_mod, "amidar", n, 60, 12)
     rng = np.random.default_rng(5)
@@ -257,6 +267,18 @@ def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
                     tiles[y][x] = "Painted"
         for b in js["board"]["boxes"][: i % 7]:
             b["painted"] = True
+        if i % 5 == 1:
+            js["player"]["position"] = {"x": int(rng.integers(-200, 2200)), "y": int(rng.integers(-200, 2600))}
+            for e in js["enemies"][:3]:
+                e["position"] = {"x": int(rng.integers(0, 1984)), "y": int(rng.integers(0, 2400))}
+        if i % 5 == 2:
+            js["enemies"] = js["enemies"][:2]
+            js["enemies"][0]["caught"] = True
+            js["score"], js["lives"], js["jumps"] = int(rng.integers(0, 99999)), int(rng.integers(0, 20)), int(rng.integers(0, 10))
+        if i % 5 == 3:
+            for row in tiles[::3]:
+                for x in range(0, 32, 2):
+                    row[x] = "Empty" if row[x] != "Empty" else "Unpainted"           # checkerboard damage: every look next to every other
         ref.write_state_json(i, js)
         states.append(js)
     pool.write_state_json(states)
@@ -264,7 +286,7 @@ def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
     try:
         for mode, omode in (("gray84", "gray84"), ("rgb", "rgb"), ("gray", "gray"), ("rgba", "rgba")):
             want = ref.render(omode).reshape(n, -1)
-            for v in ({}, {"TBX_NATIVE_KERNEL": "canvas"}, {"TBX_NATIVE_DENSE": "-1"}, {"TBX_NATIVE_DENSE": "4"}, {"TBX_AREA_LCAP": "16"},
+            for v in ({}, TILE, {"TBX_NATIVE_KERNEL": "canvas"}, {"TBX_NATIVE_DENSE": "-1"}, {"TBX_NATIVE_DENSE": "4"}, dict(TILE, TBX_AREA_LCAP="16"),
                       {"TBX_AREA_KERNEL": "cta"}):
                 for k in keys:
                     os.environ.pop(k, None)

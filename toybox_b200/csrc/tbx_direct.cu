@@ -21,6 +21,14 @@ cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, 
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*d_aux, aux.data(), sizeof(TbxBrkDirect), cudaMemcpyHostToDevice);
   }
+  if (c.game == TBX_AMIDAR) {
+    std::vector<TbxAmiDirect> aux(1);
+    tbx::build_ami_direct(c, rs, plan, aux[0]);
+    if (!aux[0].ok) return cudaSuccess;
+    e = cudaMalloc(d_aux, sizeof(TbxAmiDirect));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d_aux, aux.data(), sizeof(TbxAmiDirect), cudaMemcpyHostToDevice);
+  }
   if (c.game == TBX_SPACE_INVADERS) {
     std::vector<TbxSiDirect> aux(1);
     std::vector<TbxSpritePatch> patches;
@@ -44,6 +52,10 @@ void tbx_direct_geometry(int game, int out_w, int out_h, DirectArgs &d) {
     /* per warp: its env's record, the wall's H rows, the movers' records; two record stages */
     d.warp_bytes = align16(TBX_WORDS(BrkRec) * 4) + align16(TBX_BRK_MAX_ROWS * d.hstride * (int)sizeof(float)) + 256;
     d.smem_total = d.smem_base + 2 * TBX_WORDS(BrkRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
+  } else if (game == TBX_AMIDAR) {
+    /* per warp: its env's record, the tile rows as looks, the movers' records; two record stages */
+    d.warp_bytes = align16(TBX_WORDS(AmiRec) * 4) + 256 + 448;
+    d.smem_total = d.smem_base + 2 * TBX_WORDS(AmiRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
   } else {
     /* per warp: its env's record, the entries, two coverage bitmaps, the evaluated-entry list; one record stage */
     const int ow = (out_w + 31) / 32;
@@ -91,7 +103,21 @@ template <int TX, int TY> static cudaError_t launch_si(const RenderArgs &a, cons
   return cudaGetLastError();
 }
 
+template <int TX, int TY> static cudaError_t launch_ami(const RenderArgs &a, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(ami_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
+  if (e != cudaSuccess) return e;
+  int grid = 1;
+  e = persistent_grid(ami_direct_kernel<TX, TY>, d.smem_total, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
+  if (e != cudaSuccess) return e;
+  ami_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, d.smem_total, s>>>(a, plan, d);
+  return cudaGetLastError();
+}
+
 cudaError_t tbx_launch_direct(int game, int tx, int ty, const RenderArgs &a, const void *cfg_host, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
+  if (game == TBX_AMIDAR) { /* the tables are built for tx <= 4 only */
+    if (ty <= 3) return tx <= 3 ? launch_ami<3, 3>(a, plan, d, s) : launch_ami<4, 3>(a, plan, d, s);
+    return tx <= 3 ? launch_ami<3, 4>(a, plan, d, s) : launch_ami<4, 4>(a, plan, d, s);
+  }
   if (game == TBX_SPACE_INVADERS) {
     if (ty <= 3) {
       if (tx <= 3) return launch_si<3, 3>(a, plan, d, s);

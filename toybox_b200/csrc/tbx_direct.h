@@ -173,4 +173,34 @@ typedef struct TbxSiDirect {
 } TbxSiDirect;
 /* patch of set s at phase (x mod px_period, y mod py_period): patches[(s * py_period + yphase) * px_period + xphase] */
 
+/* ------------------------------------------------------------------ Amidar: a grid of cells with four looks
+ * The maze is 32 x 31 tiles of 4 x 5 pixels; a tile looks empty (background), unpainted, painted, or -- inside a painted box --
+ * filled.  The horizontal sum of a tile row at an output column depends on the looks of at most two neighbouring tiles: a
+ * 16-entry look-up per column, shared by all tile rows (they have the same geometry).  Only the output words x rows fed by a
+ * tile whose look differs from the config board's are recomputed.  Enemies and player (6 x 7 rectangles) are evaluated like
+ * Breakout's movers, their source windows built from the tile looks. */
+#define AMI_N_MOVERS (TBX_AMI_MAX_ENEMIES + 1) /* enemies in index order, then the player (draw order) */
+typedef struct TbxAmiDirect {
+  int32_t ok;
+  int32_t mdy0, mdy1;            /* output rows fed by the maze's source rows (inclusive) */
+  int32_t hud_dylo;              /* first output row fed by a HUD digit row */
+  uint32_t gray[4];              /* look -> gray: background, unpainted, painted, box fill */
+  uint32_t player_gray, enemy_gray;
+  uint32_t base_looks[TBX_AMI_BH][2]; /* the config board as 2-bit looks (what base frame 1 shows) */
+  uint8_t xcol[TBX_AREA_MAX_SRC];     /* tile column of source column x, 255 = none */
+  uint8_t yrow[TBX_AREA_MAX_SRC];     /* tile row of source row y, 255 = none */
+  alignas(4) uint8_t col0[TBX_AREA_MAX_DST];     /* per output column: its taps touch tile columns col0 and col0 + 1 only */
+  uint8_t ysel[TBX_AREA_MAX_DST][TBX_AREA_MAX_TAPS]; /* per output row and tap: tile row, 255 = a background row */
+  uint32_t dyrows[TBX_AREA_MAX_DST];  /* per output row: mask of the tile rows its taps touch */
+  uint32_t wordcols[32][2];           /* per output word: the tile columns that feed it, as a mask over the 2-bit look fields */
+  uint32_t inv32[TBX_AREA_MAX_DST + 1];
+  alignas(16) float hlut[16][TBX_AREA_MAX_DST]; /* [look(col0) | look(col0 + 1) << 2][dx] */
+} TbxAmiDirect;
+
+/* tile tags (2 bits each, 16 per word) -> looks: Empty 0, Unpainted / ChaseMarker 1, Painted 2 */
+TBX_HD uint32_t ami_looks_of_tags(uint32_t t) {
+  const uint32_t hi = (t >> 1) & 0x55555555u, lo = t & 0x55555555u, both = hi & lo;
+  return ((hi | lo) & ~both) | (both << 1);
+}
+
 #endif

@@ -1112,4 +1112,67 @@ void build_si_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &pl
   patches.swap(out);
 }
 
+/* Amidar: look-up tables of the direct kernel for one output size (tbx_direct.h) */
+void build_ami_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &pl, TbxAmiDirect &A) {
+  memset(&A, 0, sizeof A);
+  const int W = TBX_AMI_W, H = TBX_AMI_H, dw = pl.dw, dh = pl.dh;
+  if (c.game != TBX_AMIDAR || dw % 4 != 0 || dw > TBX_AREA_MAX_DST || dh > TBX_AREA_MAX_DST || pl.tx > 4 || pl.ty > 4) return;
+  const AmiCfg &cf = c.ami;
+  A.gray[0] = tbx_luma(cf.bg_color); A.gray[1] = tbx_luma(cf.unpainted_color); A.gray[2] = tbx_luma(cf.painted_color); A.gray[3] = tbx_luma(cf.inner_painted_color);
+  A.player_gray = tbx_luma(cf.player_color); A.enemy_gray = tbx_luma(cf.enemy_color);
+  for (int ty = 0; ty < TBX_AMI_BH; ty++) for (int k = 0; k < 2; k++) A.base_looks[ty][k] = ami_looks_of_tags(cf.board[ty][k]);
+  for (int k = 2; k <= TBX_AREA_MAX_DST; k++) A.inv32[k] = 0xffffffffu / (uint32_t)k + 1u;
+  memset(A.xcol, 255, sizeof A.xcol);
+  memset(A.yrow, 255, sizeof A.yrow);
+  const int mx0 = AMI_OFF_X, mx1 = AMI_OFF_X + 4 * TBX_AMI_BW, my0 = AMI_OFF_Y, my1 = AMI_OFF_Y + 5 * TBX_AMI_BH;
+  if (mx1 > W || my1 > H) return;
+  for (int x = mx0; x < mx1; x++) A.xcol[x] = (uint8_t)((x - mx0) / 4);
+  for (int y = my0; y < my1; y++) A.yrow[y] = (uint8_t)((y - my0) / 5);
+  std::vector<uint8_t> row(W);
+  for (int dx = 0; dx < dw; dx++) {
+    int cmin = 255, cmax = -1;
+    for (int k = rs.x.start[dx]; k < rs.x.start[dx + 1]; k++) {
+      const int cc = A.xcol[rs.x.si[k]];
+      if (cc == 255) continue;
+      A.wordcols[dx >> 2][cc >> 4] |= 3u << (2 * (cc & 15));
+      if (cc < cmin) cmin = cc;
+      if (cc > cmax) cmax = cc;
+    }
+    if (cmax >= 0 && cmax - cmin > 1) return;
+    int c0 = cmax < 0 ? 0 : cmin;
+    if (c0 > TBX_AMI_BW - 2) c0 = TBX_AMI_BW - 2;
+    A.col0[dx] = (uint8_t)c0;
+    for (int idx = 0; idx < 16; idx++) {
+      std::fill(row.begin(), row.end(), (uint8_t)A.gray[0]);
+      for (int j = 0; j < 2; j++) {
+        const int look = (idx >> (2 * j)) & 3;
+        for (int x = mx0 + 4 * (c0 + j); x < mx0 + 4 * (c0 + j + 1); x++) row[x] = (uint8_t)A.gray[look];
+      }
+      A.hlut[idx][dx] = hsum_row(row.data(), W, pl, dx);
+    }
+  }
+  A.mdy0 = pl.ydlo[my0]; A.mdy1 = pl.ydhi[my1 - 1];
+  for (int dy = 0; dy < dh; dy++) {
+    const int nreal = rs.y.start[dy + 1] - rs.y.start[dy];
+    for (int k = 0; k < TBX_AREA_MAX_TAPS; k++) {
+      if (k >= nreal) { A.ysel[dy][k] = A.ysel[dy][0]; continue; }
+      const int r = A.yrow[pl.ys0[dy] + k];
+      A.ysel[dy][k] = (uint8_t)r;
+      if (r != 255) A.dyrows[dy] |= 1u << r;
+    }
+  }
+  { /* HUD digit rows (score, lives, jumps) lie below the maze */
+    std::vector<uint32_t> rec(TBX_WORDS(AmiRec), 0);
+    TbxHdr &h = *reinterpret_cast<TbxHdr *>(rec.data());
+    h.score = 1999999999; h.lives = 1999999999;
+    reinterpret_cast<AmiRec *>(rec.data())->jumps = 1999999999;
+    int y0 = H;
+    for (int s = AMI_SLOT_SCORE; s < AMI_N_SLOTS; s++) { const TbxPrim p = ami_prim(rec.data(), cf, 0, s); if (p.h > 0 && p.y < y0) y0 = p.y; }
+    if (y0 < 0) y0 = 0;
+    A.hud_dylo = y0 < H ? pl.ydlo[y0] : dh;
+    if (A.hud_dylo <= A.mdy1) return;
+  }
+  A.ok = 1;
+}
+
 } /* namespace tbx */

@@ -11,6 +11,7 @@
 
 struct TbxBrkDirect; /* tbx_direct.h */
 struct TbxSiDirect;
+struct TbxAmiDirect;
 struct TbxSpritePatch;
 
 namespace tbx {
@@ -90,6 +91,7 @@ void build_digit_patches(const Config &c, const BrkTable *brk_default, const Res
 void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray, TbxBrkDirect &out);
 /* Space Invaders: plain-background map and pre-resolved sprite patch tables of the direct kernel (tbx_direct.h) */
 void build_si_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray, TbxSiDirect &out, std::vector<TbxSpritePatch> &patches);
+void build_ami_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &plan, TbxAmiDirect &out); /* Amidar: tile-look tables of the direct kernel */
 int digit_slot0(int game);   /* first draw-list slot of the HUD digit fields */
 int digit_slots(int game);   /* how many consecutive digit slots follow */
 

@@ -31,26 +31,21 @@ struct StepArgs {
   int *bad_actions;
 };
 
-/* Thread per env.  The env's record is STAGED IN SHARED MEMORY first: between two steps the render kernel writes hundreds of MB
- * of observations, so the state planes are no longer in L2, and a transition that reads them field by field is a chain of
- * dependent DRAM round trips (measured: 86 cycles per warp instruction, 11 % issue-active).  Staged, every state word of the
- * block travels in one burst of independent, coalesced loads (word w of 32 consecutive envs = one 128-byte line); the transition
- * then runs on shared memory (column `tid`, stride EPB words: conflict-free) and only the words it changed are written back. */
+/* Thread per env, two variants.
+ * STAGED: the block's records are brought into shared memory first.  Between two steps the render kernel writes hundreds of MB of
+ * observations, so the state planes are no longer in L2, and a transition that reads them field by field is a chain of dependent
+ * DRAM round trips (Breakout, measured: 86 cycles per warp instruction, 11 % issue-active).  Staged, every state word of the block
+ * travels as 16-byte asynchronous copies (cp.async, all in flight at once: word w of the block's envs is one contiguous run), the
+ * transition runs on shared memory (column `tid`, stride EPB words: conflict-free) and the columns are stored back, coalesced.
+ * LAZY: the transition reads and writes the planes directly.
+ * Measured per 65,536 envs in steady state (profiles/r2_step_variants.md): Space Invaders -- whose transition walks its 36 invaders
+ * several times -- 90 us staged against 178 us lazy; Breakout 39 / 37 us and Amidar 69 / 61 us gain nothing (their time is f64
+ * latency and divergence, not memory), so only Space Invaders is staged by default. */
 template <int GAME> struct StepGeom { static constexpr int EPB = Traits<GAME>::RW * 128 * 4 <= 48 * 1024 ? 128 : Traits<GAME>::RW * 64 * 4 <= 64 * 1024 ? 64 : 32; };
+
 template <int GAME>
-__global__ void __launch_bounds__(StepGeom<GAME>::EPB) step_kernel(StepArgs a) {
+__device__ __forceinline__ void step_env(const StepArgs &a, const TbxAcc &S, int env) {
   typedef Traits<GAME> T;
-  constexpr int EPB = StepGeom<GAME>::EPB, RW = T::RW;
-  extern __shared__ uint32_t srec[]; /* [RW][EPB] */
-  const int tid = threadIdx.x, env = blockIdx.x * EPB + tid;
-  if (env >= a.n) return;
-  const uint32_t *gcol = a.planes + env;
-  uint32_t *scol = srec + tid;
-#pragma unroll 8
-  for (int w = 0; w < RW; w++) scol[w * EPB] = gcol[(size_t)w * a.n_pad];
-  TbxAcc S;
-  S.p = scol;
-  S.stride = (size_t)EPB;
   const typename T::Cfg &cfg = *(const typename T::Cfg *)a.cfg;
   const typename T::Table *tables = (const typename T::Table *)a.tables;
   int in = a.actions ? tbx_ale_action_to_input(a.actions[env])
@@ -71,13 +66,45 @@ __global__ void __launch_bounds__(StepGeom<GAME>::EPB) step_kernel(StepArgs a) {
     atomicMax((long long *)(a.stats + 3), (long long)o.ep_return);
   }
   if (o.done && a.auto_reset) T::new_game(S, cfg, tables);
-  /* write back what changed (the planes' lines are in L2 now: the compare costs no DRAM traffic) */
-  uint32_t *wcol = a.planes + env;
-#pragma unroll 8
-  for (int w = 0; w < RW; w++) {
-    const uint32_t v = scol[w * EPB];
-    if (v != wcol[(size_t)w * a.n_pad]) wcol[(size_t)w * a.n_pad] = v;
+}
+
+template <int GAME>
+__global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.n) return;
+  TbxAcc S;
+  S.p = a.planes + env;
+  S.stride = (size_t)a.n_pad;
+  step_env<GAME>(a, S, env);
+}
+
+template <int GAME>
+__global__ void __launch_bounds__(StepGeom<GAME>::EPB) step_staged_kernel(StepArgs a) {
+  constexpr int EPB = StepGeom<GAME>::EPB, RW = Traits<GAME>::RW, CPW = EPB / 4; /* 16-byte chunks per state word */
+  extern __shared__ uint4 srec_raw[];
+  uint32_t *srec = reinterpret_cast<uint32_t *>(srec_raw); /* [RW][EPB] */
+  const int tid = threadIdx.x, env0 = blockIdx.x * EPB, env = env0 + tid;
+  /* n_pad is a multiple of 32 and the planes are padded, so whole 16-byte chunks are readable; EPB divides n_pad or the grid's
+   * last block is clipped to the padded range */
+  const int n_chunks = min(EPB, a.n_pad - env0) / 4;
+  for (int i = tid; i < RW * CPW; i += EPB) {
+    const int w = i / CPW, c = i - w * CPW;
+    if (c < n_chunks)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(srec + w * EPB + 4 * c)),
+                   "l"(a.planes + (size_t)w * a.n_pad + env0 + 4 * c) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (env >= a.n) return;
+  uint32_t *scol = srec + tid;
+  TbxAcc S;
+  S.p = scol;
+  S.stride = (size_t)EPB;
+  step_env<GAME>(a, S, env);
+  uint32_t *gcol = a.planes + env;
+#pragma unroll 8
+  for (int w = 0; w < RW; w++) gcol[(size_t)w * a.n_pad] = scol[w * EPB];
 }
 
 template <int GAME>

@@ -538,14 +538,24 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
         const bool in_state = (o & TBX_PRIM_STATE) != 0;
         const int ro = in_state ? (int)(o & 0x7fffu) : (int)o;
         const int sc = spr >> 24, sx = sc & 15, sy = sc >> 4;
-        if (bw == 16 && sc == 0x11) { /* 16 pixels per row at scale 1: shift the row's bits under the window */
+        if (bw * sx <= 16) { /* at most 16 pixels per row (zoomed HUD digits included): shift the row's bits under the window */
           const int dd = xs - ox;
+          const uint32_t iy = d_inv16[sy];
 #pragma unroll
           for (int k = 0; k < TY; k++)
             if (k >= ka && k < kb) {
-              const int ry = ys + k - oy;
+              const int py = ys + k - oy;
+              const int ry = sy == 1 ? py : (int)(((uint32_t)py * iy) >> 16);
               const uint32_t bits = in_state ? R[ro + ry] : __ldg(&d_bank[ro + ry]);
-              const uint32_t rev = __brev(bits << 16); /* pixel q of the row at bit q */
+              uint32_t row16; /* the row's pixels, left-aligned in 16 bits */
+              if (sx == 1) row16 = bits << (16 - bw);
+              else {
+                row16 = 0;
+                const uint32_t run = (1u << sx) - 1u;
+                for (int j = 0; j < bw; j++)
+                  if ((bits >> (bw - 1 - j)) & 1u) row16 |= run << (16 - (j + 1) * sx);
+              }
+              const uint32_t rev = __brev(row16 << 16); /* pixel q of the row at bit q */
               const uint32_t m5 = (dd >= 0 ? rev >> dd : rev << (-dd)) & 31u;
               const uint32_t bm = (((m5 & 15u) * 0x00204081u) & 0x01010101u) * 255u;
               lo[k] = (lo[k] & ~bm) | (g4 & bm);
@@ -553,7 +563,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
             }
           return;
         }
-        /* any other sprite (zoomed HUD digits that touch something): tap by tap */
+        /* wider zoomed sprites (none in the games' draw lists; interventions cannot create them either): tap by tap */
         const uint32_t ix = d_inv16[sx], iy = d_inv16[sy];
         for (int k = ka; k < kb; k++) {
           const int py = ys + k - oy;
@@ -593,6 +603,277 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       }
       const int iv = tbx_f2i_rn_small(acc);
       if (act) out[dy * dw + dx] = (uint8_t)(iv > 255 ? 255 : iv);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ Amidar: the maze as a grid of looks (tbx_direct.h)
+ * Same persistent frame as the Breakout kernel.  Per env (warp):
+ *   1. frame <- down-sample of base frame 1 (the config board), one bulk copy;
+ *   2. lane ty turns tile row ty into 2-bit looks (painted boxes fill their interior) and compares it with the board's: the
+ *      output words x rows fed by a changed tile are recomputed -- horizontal sums by table look-up (two neighbouring looks and
+ *      the output column), vertical taps over the tile rows; cost bounded by the maze's output area, however much is painted;
+ *   3. HUD digits (score, lives, jumps): pre-resolved patches;
+ *   4. enemies and player: the output pixels their 6 x 7 rectangles feed, source windows built from the tile looks. */
+template <int TX, int TY>
+__global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ TbxAreaPlan plan_c,
+                                                                                          const __grid_constant__ DirectArgs d) {
+  constexpr int RW = TBX_WORDS(AmiRec), W = TBX_AMI_W, H = TBX_AMI_H;
+  constexpr int RECW_BYTES = (RW * 4 + 15) & ~15;
+  extern __shared__ uint4 smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
+  uint8_t *sbase = smem;
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base); /* [2][RW][8 envs] */
+  const TbxAmiDirect *__restrict__ Ap = reinterpret_cast<const TbxAmiDirect *>(d.aux);
+  const TbxAmiDirect &A = *Ap;
+  const AmiTable *__restrict__ tables = reinterpret_cast<const AmiTable *>(a.tables);
+  const TbxAreaPlan *__restrict__ plan = a.plan;
+  const TbxAreaPlan &cp = plan_c;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint8_t *wmem = smem + d.smem_base + 2 * RW * TBX_EPC * 4 + wid * d.warp_bytes;
+  uint32_t *recw = reinterpret_cast<uint32_t *>(wmem);
+  uint32_t *lk = reinterpret_cast<uint32_t *>(wmem + RECW_BYTES);             /* [31][2]: the tile rows as 2-bit looks */
+  int4 *mrec = reinterpret_cast<int4 *>(wmem + RECW_BYTES + 256);             /* 3 x int4 per mover */
+  const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
+  const int dw = cp.dw, dh = cp.dh, nwords = dw >> 2, nb = dw * dh;
+  const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
+  const int ok = A.ok, mdy0 = A.mdy0, mdy1 = A.mdy1, hud_dylo = A.hud_dylo;
+  const uint32_t g0 = A.gray[0], g1 = A.gray[1], g2 = A.gray[2], g3 = A.gray[3], player_gray = A.player_gray, enemy_gray = A.enemy_gray;
+  const TbxDigitPatch *__restrict__ patches = a.patches[1];
+
+  auto prefetch = [&](int chunk, int st) {
+    const uint32_t *src = a.planes + (size_t)chunk * TBX_EPC;
+    uint32_t *dst = stage + st * RW * TBX_EPC;
+    for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(dst + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
+  for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t *R = recw;
+
+  int st = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, st ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x, st ^ 1);
+    const int env = chunk * TBX_EPC + wid;
+    if (env >= a.n) continue;
+    {
+      const uint32_t *src = stage + st * RW * TBX_EPC + wid;
+      for (int w = lane; w < RW; w += 32) recw[w] = src[w * TBX_EPC];
+    }
+    __syncwarp();
+    uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
+    /* movers: lanes 0..7 the enemies, lane 8 the player (draw order) */
+    TbxMover mine; mine.x0 = mine.y0 = mine.x1 = mine.y1 = 0; mine.gray = lane == TBX_AMI_MAX_ENEMIES ? player_gray : enemy_gray;
+    if (lane < AMI_N_MOVERS) {
+      const int m = lane == TBX_AMI_MAX_ENEMIES ? AMI_PLAYER : AMI_ENEMY(lane);
+      const bool shown = lane == TBX_AMI_MAX_ENEMIES || (lane < (int32_t)R[AMI_W(n_enemies)] && !(int32_t)R[m + AMI_MW(caught)]);
+      if (shown) {
+        const int px = AMI_OFF_X + ami_floordiv((int32_t)R[m + AMI_MW(x)], 16) - 1, py = AMI_OFF_Y + ami_floordiv((int32_t)R[m + AMI_MW(y)], 16) - 1;
+        const TbxPrim p = tbx_prim_rect(0, px, py, 6, 7); /* clamps far-away coordinates like the draw list does */
+        if (p.h > 0) {
+          mine.x0 = max((int)p.x, 0); mine.y0 = max((int)p.y, 0); mine.x1 = min((int)p.x + (int)p.w, W); mine.y1 = min((int)p.y + (int)p.h, H);
+          if (mine.x0 >= mine.x1 || mine.y0 >= mine.y1) mine.x0 = mine.x1 = 0;
+        }
+      }
+    }
+    const bool valid = mine.x0 < mine.x1;
+    int fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;
+    if (valid) { fx0 = __ldg(&plan->xdlo[mine.x0]); fx1 = __ldg(&plan->xdhi[mine.x1 - 1]); fy0 = __ldg(&plan->ydlo[mine.y0]); fy1 = __ldg(&plan->ydhi[mine.y1 - 1]); }
+    bool bad = valid && fy1 >= hud_dylo;
+    /* HUD digits: lanes 0..9 the score, 10..19 the lives, 20..29 the jumps */
+    int dig = -1;
+    const TbxDigitPatch *P = patches;
+    if (lane < 3 * TBX_MAX_DIGITS && patches) {
+      const int field = lane / TBX_MAX_DIGITS;
+      const int32_t v = field == 0 ? (int32_t)R[TBX_HW(score)] : field == 1 ? (int32_t)R[TBX_HW(lives)] : (int32_t)R[AMI_W(jumps)];
+      dig = tbx_digit_at(v, lane - field * TBX_MAX_DIGITS);
+      if (dig >= 0) { P = patches + lane * 10 + dig; bad |= __ldg(&P->w) == 0; }
+    }
+    if (!ok || !patches || __any_sync(0xffffffffu, bad)) { /* the general kernel's */
+      if (lane == 0) d.fb_list[atomicAdd(d.fb_count, 1)] = env;
+      continue;
+    }
+    if (bulk) {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"((uint32_t)__cvta_generic_to_shared(sbase)), "r"((uint32_t)nb) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int i = lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(sbase)[i];
+    }
+    /* 2. looks of tile row `lane`, and what differs from the config board */
+    uint32_t l0 = 0, l1 = 0, d0 = 0, d1 = 0;
+    if (lane < TBX_AMI_BH) {
+      l0 = ami_looks_of_tags(R[AMI_W(tiles) + 2 * lane]);
+      l1 = ami_looks_of_tags(R[AMI_W(tiles) + 2 * lane + 1]);
+      uint32_t boxes = R[AMI_W(box_painted)];
+      if (boxes) {
+        const AmiTable &T = tables[(int32_t)R[TBX_HW(tbl)]];
+        boxes &= __ldg(&T.all_boxes);
+        while (boxes) { /* a painted box fills its interior, over whatever tiles lie there (draw order: boxes after tiles) */
+          const int b = __ffs(boxes) - 1;
+          boxes &= boxes - 1;
+          const int tlx = __ldg(&T.tl_tx[b]), tly = __ldg(&T.tl_ty[b]), brx = __ldg(&T.br_tx[b]), bry = __ldg(&T.br_ty[b]);
+          if (lane > tly && lane < bry && brx - tlx > 1) {
+            const int ca = max(tlx + 1, 0), cb = min(brx - 1, TBX_AMI_BW - 1); /* tile columns ca..cb */
+            if (ca <= cb) {
+              const unsigned long long m64 = ((cb - ca + 1 >= 32 ? ~0ull : (1ull << (2 * (cb - ca + 1))) - 1ull)) << (2 * ca);
+              l0 |= (uint32_t)m64; l1 |= (uint32_t)(m64 >> 32);
+            }
+          }
+        }
+      }
+      d0 = l0 ^ __ldg(&A.base_looks[lane][0]);
+      d1 = l1 ^ __ldg(&A.base_looks[lane][1]);
+      d0 = (d0 | (d0 >> 1)) & 0x55555555u; d0 |= d0 << 1; /* both bits of a changed tile */
+      d1 = (d1 | (d1 >> 1)) & 0x55555555u; d1 |= d1 << 1;
+      lk[2 * lane] = l0; lk[2 * lane + 1] = l1;
+    }
+    const uint32_t rowsm = __ballot_sync(0xffffffffu, (d0 | d1) != 0);  /* tile rows with a changed tile */
+    const uint32_t c0m = __reduce_or_sync(0xffffffffu, d0), c1m = __reduce_or_sync(0xffffffffu, d1); /* changed tile columns (look fields) */
+    /* 4a. the movers, prepared while the base copy is in flight */
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid) & ((1u << AMI_N_MOVERS) - 1u);
+    if (lane < AMI_N_MOVERS) {
+      const int ncol = valid ? fx1 - fx0 + 1 : 0, nrow = valid ? fy1 - fy0 + 1 : 0;
+      mrec[3 * lane + 0] = make_int4(mine.x0, mine.y0, mine.x1, mine.y1);
+      mrec[3 * lane + 1] = make_int4((int)mine.gray * 0x01010101, fx0, fy0, ncol);
+      mrec[3 * lane + 2] = make_int4(ncol * nrow, ncol > 1 ? (int)__ldg(&A.inv32[ncol]) : 0, 0, 0);
+    }
+    __syncwarp();
+    int total = 0;
+#pragma unroll
+    for (int m = 0; m < AMI_N_MOVERS; m++) total += mrec[3 * m + 2].x;
+    auto mover_pixel = [&](int p0, int &o) -> uint32_t {
+      const int l = p0 + lane;
+      int mym = 0, myi = 0, off = 0;
+#pragma unroll
+      for (int m = 0; m < AMI_N_MOVERS; m++) {
+        const int cnt = mrec[3 * m + 2].x;
+        if (l >= off && l < off + cnt) { mym = m; myi = l - off; }
+        off += cnt;
+      }
+      const bool act = l < total;
+      const int4 f = mrec[3 * mym + 1];
+      const int ncol = f.w, inv = mrec[3 * mym + 2].y;
+      const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, (unsigned)inv) : myi;
+      const int dx = act ? f.y + myi - q * ncol : 0, dy = act ? f.z + q : 0;
+      o = act ? dy * dw + dx : -1;
+      const int xs = __ldg(&plan->xs0[dx]), ys = __ldg(&plan->ys0[dy]);
+      /* the source window from the tile looks: packed bytes, taps 0..3 of each row */
+      uint32_t cb[TX], lo[TY];
+#pragma unroll
+      for (int t = 0; t < TX; t++) cb[t] = __ldg(&A.xcol[min(xs + t, W - 1)]);
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        const uint32_t r = __ldg(&A.yrow[min(ys + k, H - 1)]);
+        uint32_t row = g0 * 0x01010101u;
+        if (r != 255u) {
+          const uint32_t w0 = lk[2 * r], w1 = lk[2 * r + 1];
+#pragma unroll
+          for (int t = 0; t < TX; t++)
+            if (cb[t] != 255u) {
+              const uint32_t look = ((cb[t] < 16u ? w0 >> (2 * cb[t]) : w1 >> (2 * (cb[t] - 16u)))) & 3u;
+              const uint32_t g = look == 0 ? g0 : look == 1 ? g1 : look == 2 ? g2 : g3;
+              row = (row & ~(255u << (8 * t))) | (g << (8 * t));
+            }
+        }
+        lo[k] = row;
+      }
+      uint32_t mleft = vm;
+      while (mleft) { /* draw order: enemies, then the player */
+        const int m = __ffs(mleft) - 1;
+        mleft &= mleft - 1;
+        const int4 rc = mrec[3 * m];
+        const uint32_t g4 = (uint32_t)mrec[3 * m + 1].x;
+        const int ta = max(rc.x - xs, 0), tb = min(rc.z - xs, TX), ka = max(rc.y - ys, 0), kb = min(rc.w - ys, TY);
+        if (ta >= tb || ka >= kb) continue;
+        const uint32_t below_b = tb >= 4 ? 0xffffffffu : (1u << (8 * tb)) - 1u, below_a = ta >= 4 ? 0xffffffffu : (1u << (8 * ta)) - 1u;
+        const uint32_t bm = below_b & ~below_a;
+#pragma unroll
+        for (int k = 0; k < TY; k++)
+          if (k >= ka && k < kb) lo[k] = (lo[k] & ~bm) | (g4 & bm);
+      }
+      float al[TX];
+#pragma unroll
+      for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < TY; k++) {
+        float h = tbx_fmul(tbx_u8f(lo[k] & 255u), al[0]);
+#pragma unroll
+        for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f((lo[k] >> (8 * t)) & 255u), al[t]));
+        const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+        acc = k == 0 ? bh : tbx_fadd(acc, bh);
+      }
+      const int iv = tbx_f2i_rn_small(acc);
+      return (uint32_t)(iv > 255 ? 255 : iv);
+    };
+    int o_first = -1;
+    uint32_t v_first = 0;
+    if (total > 0) v_first = mover_pixel(0, o_first);
+    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp(); /* the base copy has landed */
+    /* 2b. the maze where it differs from the board */
+    if (rowsm) {
+      const uint32_t wmask = __ballot_sync(0xffffffffu, lane < nwords && ((__ldg(&A.wordcols[lane][0]) & c0m) | (__ldg(&A.wordcols[lane][1]) & c1m)) != 0);
+      if (wmask) {
+        const int naw = __popc(wmask);
+        const int lg = naw > 16 ? 5 : naw > 8 ? 4 : naw > 4 ? 3 : naw > 2 ? 2 : naw > 1 ? 1 : 0;
+        const int jw = lane & ((1 << lg) - 1), sub = lane >> lg, rpi = 32 >> lg;
+        const int myword = jw < naw ? (int)__fns(wmask, 0, jw + 1) : -1;
+        uint32_t c04 = 0;
+        if (myword >= 0) c04 = __ldg(reinterpret_cast<const uint32_t *>(A.col0) + myword); /* col0 of the word's four columns */
+        for (int dyb = mdy0; dyb <= mdy1; dyb += rpi) {
+          const int dy = dyb + sub;
+          const bool on = myword >= 0 && dy <= mdy1 && (__ldg(&A.dyrows[min(dy, dh - 1)]) & rowsm) != 0;
+          if (!on) continue;
+          float acc[4];
+#pragma unroll
+          for (int k = 0; k < TY; k++) {
+            const uint32_t r = __ldg(&A.ysel[dy][k]);
+            const uint32_t w0 = r != 255u ? lk[2 * r] : 0u, w1 = r != 255u ? lk[2 * r + 1] : 0u;
+            const float b = __ldg(&plan->yalpha[k][dy]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint32_t c0 = (c04 >> (8 * j)) & 255u;
+              const uint32_t idx = (uint32_t)((((unsigned long long)w1 << 32) | w0) >> (2 * c0)) & 15u;
+              const float p = tbx_fmul(b, __ldg(&A.hlut[idx][4 * myword + j]));
+              acc[j] = k == 0 ? p : tbx_fadd(acc[j], p);
+            }
+          }
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int iv = tbx_f2i_rn_small(acc[j]);
+            word |= (uint32_t)(iv > 255 ? 255 : iv) << (8 * j);
+          }
+          *reinterpret_cast<uint32_t *>(out + dy * dw + 4 * myword) = word;
+        }
+      }
+    }
+    /* 3. HUD digits */
+    {
+      uint32_t dm = __ballot_sync(0xffffffffu, dig >= 0);
+      while (dm) {
+        const int l = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const TbxDigitPatch *Q = reinterpret_cast<const TbxDigitPatch *>(__shfl_sync(0xffffffffu, (unsigned long long)P, l));
+        const int px0 = __ldg(&Q->x0), py0 = __ldg(&Q->y0), pw = __ldg(&Q->w), ph = __ldg(&Q->h);
+        const int cc = lane & 7;
+        if (cc < pw)
+          for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = __ldg(&Q->px[r * pw + cc]);
+      }
+    }
+    __syncwarp(); /* the movers' pixels go over the maze's */
+    /* 4b. the movers' pixels */
+    if (o_first >= 0) out[o_first] = (uint8_t)v_first;
+    for (int p0 = 32; p0 < total; p0 += 32) {
+      int o;
+      const uint32_t v = mover_pixel(p0, o);
+      if (o >= 0) out[o] = (uint8_t)v;
     }
   }
 }
