@@ -460,6 +460,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    from toybox_b200 import distributed as D
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_cpus = D.bind_to_gpu_numa(local)          # pinned host buffers of the e2e leg land on the GPU's own NUMA node
     stream = torch.cuda.current_stream(dev)
     fb = obs_bytes(args.game, args.obs)
     rec_bytes = 4 * {"breakout": 72, "amidar": 366, "space_invaders": 392}[args.game]
@@ -633,6 +636,7 @@ def main():
         e2e = {"value": world * n * ke / sec, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h, "steps": ke,
                "api": "BatchedToybox.step_host -> tbx_step_host (pinned host actions in; obs, reward, done, score, lives out)",
                "pcie_gbs": pcie, "achieved_gbs": d2h * ke / sec / 1e9, "frac": (d2h * ke / sec / 1e9) / pcie,
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
                "pcie_note": "pcie_gbs = a bare pinned cudaMemcpyAsync D2H of the observation bytes per rank, all %d rank(s) copying at the "
                             "same time: the host-side ceiling of this call" % world}
         del h_obs
@@ -770,6 +774,8 @@ def main():
     roofline["native"] = native
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)       # the CPU baseline uses every host core again
         cores = os.cpu_count() or 1
         n_cpu = 64 * cores
         v1, s1 = cpu_rollout(args.game, args.obs, n_cpu, 20, cores)

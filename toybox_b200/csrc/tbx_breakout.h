@@ -121,25 +121,48 @@ TBX_HD bool brk_slice(const TbxAcc &S, const BrkCfg &c, const BrkTable &T, BrkBa
   }
   /* bricks: first alive brick in index order whose box meets the ball's box */
   if (xr > T.bb_x0 && xl < T.bb_x1 && yb > T.bb_y0 && yt < T.bb_y1) {
-    bool hit = false;
-    for (int k = 0; k < 5 && !hit; k++) {
-      uint32_t m = alive[k];
-      while (m) {
-        int bit = tbx_ffs(m) - 1, i = 32 * k + bit;
-        m &= m - 1;
-        if (xr > T.px[i] && xl < T.x1[i] && yb > T.py[i] && yt < T.y1[i]) {
-          if ((T.destructible[k] >> bit) & 1u) { alive[k] &= ~(1u << bit); score += T.points[i]; }
-          b.vy = -b.vy;
-          if (T.depth[i] >= c.ball_speed_row_depth) {
-            double mag = brk_vmag(b.vx, b.vy);
-            if (mag > 0.0) {
-              double ux = tbx_ddiv(b.vx, mag), uy = tbx_ddiv(b.vy, mag);
-              b.vx = tbx_dmul(ux, c.ball_speed_fast);
-              b.vy = tbx_dmul(uy, c.ball_speed_fast);
-            }
-          }
-          hit = true;
-          break;
+    int hit_i = -1;
+    if (T.grid) {
+      /* a regular column-major grid: only the cells around the ball can meet its box.  The cell range is a superset (one cell
+       * of margin absorbs the rounding of the multiply), every candidate takes the exact test, and columns then rows ascending
+       * IS index order: the same first hit as the full scan below. */
+      int c0 = tbx_d2i(tbx_dmul(tbx_dsub(xl, T.gx0), T.ginv_w)) - 1, c1 = tbx_d2i(tbx_dmul(tbx_dsub(xr, T.gx0), T.ginv_w)) + 1;
+      int r0 = tbx_d2i(tbx_dmul(tbx_dsub(yt, T.gy0), T.ginv_h)) - 1, r1 = tbx_d2i(tbx_dmul(tbx_dsub(yb, T.gy0), T.ginv_h)) + 1;
+      if (c0 < 0) c0 = 0;
+      if (r0 < 0) r0 = 0;
+      if (c1 > T.g_ncols - 1) c1 = T.g_ncols - 1;
+      if (r1 > T.g_nrows - 1) r1 = T.g_nrows - 1;
+      for (int c = c0; c <= c1 && hit_i < 0; c++)
+        for (int r = r0; r <= r1; r++) {
+          const int i = c * T.g_nrows + r, k = i >> 5;
+          const uint32_t w = k == 0 ? alive[0] : k == 1 ? alive[1] : k == 2 ? alive[2] : k == 3 ? alive[3] : alive[4];
+          if (!((w >> (i & 31)) & 1u)) continue;
+          if (xr > T.px[i] && xl < T.x1[i] && yb > T.py[i] && yt < T.y1[i]) { hit_i = i; break; }
+        }
+    } else {
+      for (int k = 0; k < 5 && hit_i < 0; k++) {
+        uint32_t m = alive[k];
+        while (m) {
+          int bit = tbx_ffs(m) - 1, i = 32 * k + bit;
+          m &= m - 1;
+          if (xr > T.px[i] && xl < T.x1[i] && yb > T.py[i] && yt < T.y1[i]) { hit_i = i; break; }
+        }
+      }
+    }
+    if (hit_i >= 0) {
+      const int i = hit_i, k = i >> 5, bit = i & 31;
+      const uint32_t destr = k == 0 ? T.destructible[0] : k == 1 ? T.destructible[1] : k == 2 ? T.destructible[2] : k == 3 ? T.destructible[3] : T.destructible[4];
+      if ((destr >> bit) & 1u) {
+        for (int q = 0; q < 5; q++) if (q == k) alive[q] &= ~(1u << bit);
+        score += T.points[i];
+      }
+      b.vy = -b.vy;
+      if (T.depth[i] >= c.ball_speed_row_depth) {
+        double mag = brk_vmag(b.vx, b.vy);
+        if (mag > 0.0) {
+          double ux = tbx_ddiv(b.vx, mag), uy = tbx_ddiv(b.vy, mag);
+          b.vx = tbx_dmul(ux, c.ball_speed_fast);
+          b.vy = tbx_dmul(uy, c.ball_speed_fast);
         }
       }
     }

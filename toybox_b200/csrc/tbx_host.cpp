@@ -189,6 +189,21 @@ void brk_finish_table(BrkTable &t) {
   /* NaN coordinates never compare true in the step; make the early-out box permissive in that case */
   if (!(t.bb_x0 == t.bb_x0) || !(t.bb_y0 == t.bb_y0) || !(t.bb_x1 == t.bb_x1) || !(t.bb_y1 == t.bb_y1)) { t.bb_x0 = t.bb_y0 = -INFINITY; t.bb_x1 = t.bb_y1 = INFINITY; }
   for (int i = 0; i < n; i++) if (t.px[i] != t.px[i] || t.py[i] != t.py[i] || t.x1[i] != t.x1[i] || t.y1[i] != t.y1[i]) { t.bb_x0 = t.bb_y0 = -INFINITY; t.bb_x1 = t.bb_y1 = INFINITY; }
+  /* regular column-major grid?  (the default table always is; a table edited through JSON usually is not) */
+  t.grid = 0; t.g_ncols = t.g_nrows = 0; t._padg = 0; t.gx0 = t.gy0 = t.ginv_w = t.ginv_h = 0.0;
+  if (n > 0 && t.sx[0] > 0.0 && t.sy[0] > 0.0) {
+    int nrows = 1;
+    while (nrows < n && t.px[nrows] == t.px[0]) nrows++;
+    if (n % nrows == 0) {
+      const int ncols = n / nrows;
+      bool ok = true;
+      for (int i = 0; i < n && ok; i++) {
+        const int col = i / nrows, row = i % nrows;
+        ok = t.px[i] == t.px[0] + col * t.sx[0] && t.py[i] == t.py[0] + row * t.sy[0] && t.sx[i] == t.sx[0] && t.sy[i] == t.sy[0];
+      }
+      if (ok) { t.grid = 1; t.g_ncols = ncols; t.g_nrows = nrows; t.gx0 = t.px[0]; t.gy0 = t.py[0]; t.ginv_w = 1.0 / t.sx[0]; t.ginv_h = 1.0 / t.sy[0]; }
+    }
+  }
   t.hud_clear = 1;
   for (int i = 0; i < n; i++) if (t.iw[i] > 0 && t.ih[i] > 0 && t.iy[i] < 12) t.hud_clear = 0;
   t.disjoint = 1;

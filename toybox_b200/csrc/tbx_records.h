@@ -59,6 +59,10 @@ typedef struct {
   int32_t hud_clear;          /* no brick rect reaches into the HUD digit rows (y < 12) */
   int32_t delta_ok;           /* disjoint, HUD-clear and every brick lies on pure background: base frame 1 may hold them */
   double bb_x0, bb_y0, bb_x1, bb_y1; /* union of all brick boxes (collision early-out) */
+  /* the bricks form a regular column-major grid (index = col * g_nrows + row, brick (col, row) at (gx0 + col * gw, gy0 + row * gh)):
+   * the collision test visits only the few cells around the ball instead of every alive brick (same first hit in index order) */
+  int32_t grid, g_ncols, g_nrows, _padg;
+  double gx0, gy0, ginv_w, ginv_h;
   double px[TBX_BRK_MAX_BRICKS], py[TBX_BRK_MAX_BRICKS], sx[TBX_BRK_MAX_BRICKS], sy[TBX_BRK_MAX_BRICKS];
   double x1[TBX_BRK_MAX_BRICKS], y1[TBX_BRK_MAX_BRICKS]; /* px+sx, py+sy (same IEEE add the step does) */
   int32_t points[TBX_BRK_MAX_BRICKS], depth[TBX_BRK_MAX_BRICKS], row[TBX_BRK_MAX_BRICKS], col[TBX_BRK_MAX_BRICKS];

@@ -638,7 +638,8 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
   const int dw = cp.dw, dh = cp.dh, nwords = dw >> 2, nb = dw * dh;
   const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
   const int ok = A.ok, mdy0 = A.mdy0, mdy1 = A.mdy1, hud_dylo = A.hud_dylo;
-  const uint32_t g0 = A.gray[0], g1 = A.gray[1], g2 = A.gray[2], g3 = A.gray[3], player_gray = A.player_gray, enemy_gray = A.enemy_gray;
+  const uint32_t g0 = A.gray[0], player_gray = A.player_gray, enemy_gray = A.enemy_gray;
+  const uint32_t glut = A.gray[0] | (A.gray[1] << 8) | (A.gray[2] << 16) | (A.gray[3] << 24); /* look -> gray, one byte each */
   const TbxDigitPatch *__restrict__ patches = a.patches[1];
 
   auto prefetch = [&](int chunk, int st) {
@@ -776,7 +777,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
           for (int t = 0; t < TX; t++)
             if (cb[t] != 255u) {
               const uint32_t look = ((cb[t] < 16u ? w0 >> (2 * cb[t]) : w1 >> (2 * (cb[t] - 16u)))) & 3u;
-              const uint32_t g = look == 0 ? g0 : look == 1 ? g1 : look == 2 ? g2 : g3;
+              const uint32_t g = (glut >> (8 * look)) & 255u;
               row = (row & ~(255u << (8 * t))) | (g << (8 * t));
             }
         }

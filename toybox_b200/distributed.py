@@ -8,6 +8,30 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its PCIe root's NUMA node), so that
+    pinned host buffers allocated afterwards are first-touched there: host-facing calls (tbx_step_host) then copy over the GPU's own
+    root port instead of the inter-socket link.  Returns the CPU list it bound to, or None when NVML / affinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].strip().isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard(total_envs, rank, world):
     """Contiguous, balanced env-id range of `rank`: returns (env0, n)."""
     if not 0 <= rank < world:
