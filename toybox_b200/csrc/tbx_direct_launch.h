@@ -11,6 +11,7 @@ struct DirectArgs {
   const void *aux2;   /* Space Invaders: the sprite patch tables (TbxSpritePatch[]) */
   int32_t *fb_list;   /* envs handed to the tile kernel */
   int *fb_count;
+  int *sched;         /* [2]: next chunk id - grid size, finished CTAs (dynamic chunk scheduling of the persistent kernels) */
   int hstride;        /* floats per H row in shared memory */
   int warp_bytes;     /* shared memory per warp */
   int smem_base;      /* bytes of the staged base-frame down-sample at the start of shared memory */

@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
     for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(dst + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
     cp_async_commit();
   };
+  /* dynamic chunk scheduling: CTA b starts with chunk b, further chunks come from a device-wide counter (thread 0 draws the
+   * id one iteration ahead; the barrier at the top of the loop publishes it), so the CTAs finish together whatever their envs cost */
+  __shared__ int s_next[2];
+  if (tid == 0) s_next[0] = (int)gridDim.x + atomicAdd(d.sched, 1);
   if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk copies below read sbase through the async proxy */
@@ -76,11 +80,13 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   const TbxDigitPatch *__restrict__ patches = a.patches[1];
   const uint32_t *R = recw;
 
-  int st = 0;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, st ^= 1) {
+  int st = 0, it = 0, nxt = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk = nxt, st ^= 1, it++) {
     cp_async_wait_all();
-    __syncthreads(); /* this chunk's records have landed; every warp is done with the other stage */
-    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x, st ^ 1);
+    __syncthreads(); /* this chunk's records have landed; every warp is done with the other stage; s_next[it & 1] is visible */
+    nxt = s_next[it & 1];
+    if (nxt < n_chunks) prefetch(nxt, st ^ 1);
+    if (tid == 0) s_next[(it + 1) & 1] = (int)gridDim.x + atomicAdd(d.sched, 1);
     const int env = chunk * TBX_EPC + wid;
     if (env >= a.n) continue;
     {
@@ -300,6 +306,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
     }
   }
 #undef TBX_DIRECT_LAND
+  /* the last CTA to finish re-arms the chunk counter for the next launch */
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(d.sched + 1, 1) == (int)gridDim.x - 1) { d.sched[0] = 0; d.sched[1] = 0; __threadfence(); }
+  }
 }
 
 /* ------------------------------------------------------------------ Space Invaders: sparse sprites on a plain base
@@ -354,19 +365,24 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
     for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(stage + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
     cp_async_commit();
   };
+  __shared__ int s_next[2]; /* dynamic chunk scheduling, as in the Breakout kernel */
+  if (tid == 0) s_next[0] = (int)gridDim.x + atomicAdd(d.sched, 1);
   if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[0]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const uint32_t *R = recw;
 
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  int it = 0, nxt = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk = nxt, it++) {
     cp_async_wait_all();
-    __syncthreads(); /* the chunk's records have landed; every warp is done with its previous env */
+    __syncthreads(); /* the chunk's records have landed; every warp is done with its previous env; s_next[it & 1] is visible */
+    nxt = s_next[it & 1];
     const int env = chunk * TBX_EPC + wid;
     if (env < a.n)
       for (int w = lane; w < RW; w += 32) recw[w] = stage[w * TBX_EPC + wid];
     __syncthreads(); /* the stage is free again */
-    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x);
+    if (nxt < n_chunks) prefetch(nxt);
+    if (tid == 0) s_next[(it + 1) & 1] = (int)gridDim.x + atomicAdd(d.sched, 1);
     if (env >= a.n) continue;
     uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
     if (bulk) {
@@ -605,6 +621,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       if (act) out[dy * dw + dx] = (uint8_t)(iv > 255 ? 255 : iv);
     }
   }
+  /* the last CTA to finish re-arms the chunk counter for the next launch */
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(d.sched + 1, 1) == (int)gridDim.x - 1) { d.sched[0] = 0; d.sched[1] = 0; __threadfence(); }
+  }
 }
 
 /* ------------------------------------------------------------------ Amidar: the maze as a grid of looks (tbx_direct.h)
@@ -648,16 +669,22 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
     for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(dst + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
     cp_async_commit();
   };
+  /* dynamic chunk scheduling: CTA b starts with chunk b, further chunks come from a device-wide counter (thread 0 draws the
+   * id one iteration ahead; the barrier at the top of the loop publishes it), so the CTAs finish together whatever their envs cost */
+  __shared__ int s_next[2];
+  if (tid == 0) s_next[0] = (int)gridDim.x + atomicAdd(d.sched, 1);
   if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const uint32_t *R = recw;
 
-  int st = 0;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, st ^= 1) {
+  int st = 0, it = 0, nxt = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk = nxt, st ^= 1, it++) {
     cp_async_wait_all();
     __syncthreads();
-    if (chunk + (int)gridDim.x < n_chunks) prefetch(chunk + gridDim.x, st ^ 1);
+    nxt = s_next[it & 1];
+    if (nxt < n_chunks) prefetch(nxt, st ^ 1);
+    if (tid == 0) s_next[(it + 1) & 1] = (int)gridDim.x + atomicAdd(d.sched, 1);
     const int env = chunk * TBX_EPC + wid;
     if (env >= a.n) continue;
     {
@@ -876,6 +903,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
       const uint32_t v = mover_pixel(p0, o);
       if (o >= 0) out[o] = (uint8_t)v;
     }
+  }
+  /* the last CTA to finish re-arms the chunk counter for the next launch */
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(d.sched + 1, 1) == (int)gridDim.x - 1) { d.sched[0] = 0; d.sched[1] = 0; __threadfence(); }
   }
 }
 
