@@ -8,10 +8,16 @@ device, advance every env one frame (tbx_step), render every env (tbx_render).  
     python bench.py [--gpus N] [--steps K] [--warmup W] [--game G] [--envs E] [--obs gray84|gray|rgb|rgba]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
     python bench.py --impl reference ...    times the CPU restatement of the reference path (oracle/) on the host cores
-    python bench.py --wrapped [--game G]    supplementary: the fused DeepMind wrapper stack (agent steps/s; 1 agent step = 4 frames)
+    python bench.py --game amidar --envs 262144 --obs rgb          BASELINE configs[2]
+    python bench.py --interventions         supplementary: BASELINE configs[3], Space Invaders 262,144 envs with JSON state interventions
     python bench.py --mixed 1048576 [--gpus N under torchrun]    supplementary: BASELINE configs[4], 1/3 of the envs per game,
-                                            NCCL all-reduce of the episode statistics every 256 steps
+                                            NCCL all-reduce of the episode statistics every 256 steps (inside the timed region)
+    python bench.py --wrapped [--game G]    supplementary: the fused DeepMind wrapper stack (agent steps/s; 1 agent step = 4 frames)
     python bench.py --policy track --presteps 3000    supplementary: mid-game Breakout states (scripted ball-tracking policy)
+
+The pool is in steady state when the clock starts (--presteps 2000 untimed step-only frames, default); the line also carries the survey's
+protocol (warm-up 100, 5 x 1,000 steps: best, mean, SEM), fresh-game / mid-game sub-records, the e2e leg with its own PCIe roofline
+(raw and wrapped env), the collective's cost (N > 1) and, at 8 GPUs, the batch-1M north_star sub-record.
 """
 import argparse
 import json
@@ -25,7 +31,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GAME_DTYPE = {"breakout": "f64+u8", "amidar": "i32+u8", "space_invaders": "i32+u8"}
-STATE_BYTES = {"breakout": None, "amidar": None, "space_invaders": None}   # filled from the library's record size
 ACTION_SEED = 0xB200
 
 

@@ -246,6 +246,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
     if (gb >= ge) { prev_nosync = false; continue; } /* empty group (uniform across the CTA); its neighbour's flag does not carry over */
     const bool cur_multi = !(gmode & TBX_GROUP_SERIAL) && (ge - gb) > 32;
     if (have_prev && (prev_multi || cur_multi) && !prev_nosync) __syncthreads();
+    else if (have_prev) __syncwarp(); /* warp 0 after warp 0: orders the other lanes' stores of the earlier group before this one's */
     have_prev = true;
     prev_multi = cur_multi;
     prev_nosync = (gmode & TBX_GROUP_NOSYNC) != 0 && !cur_multi; /* a multi-warp group resets its queue: always fenced */
@@ -260,6 +261,7 @@ __device__ __forceinline__ void paint_env(const uint32_t *R, const typename Trai
         const uint32_t val = PIX == 1 ? tbx_luma(p.color) : p.color;
         const bool small = ok && p.bw == 0 && (c.x1 - c.x0) * (c.y1 - c.y0) <= 512; /* up to a column of merged dead bricks: one thread, word stores */
         if (small) paint_small<PIX, W>(canvas, r0, c, val);
+        __syncwarp(); /* lane-painted rectangles before the warp-painted ones of the same pass */
         const uint32_t w0 = (uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16), w1 = (uint16_t)p.w | ((uint32_t)(uint16_t)p.h << 16);
         const uint32_t w3 = (uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24);
         bool deferred = false;
