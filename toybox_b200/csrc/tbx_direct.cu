@@ -139,3 +139,12 @@ cudaError_t tbx_launch_direct(int game, int tx, int ty, const RenderArgs &a, con
   if (tx <= 4) return launch_brk<4, 4>(a, cfg, plan, d, s);
   return launch_brk<5, 4>(a, cfg, plan, d, s);
 }
+
+#ifdef TBX_SI_STATS
+extern "C" int tbx_debug_si_stats(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, tbxk::d_si_stats, sizeof(unsigned long long) * 48) != cudaSuccess) return 1;
+  if (reset) { unsigned long long z[48] = {0}; cudaMemcpyToSymbol(tbxk::d_si_stats, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -328,6 +328,9 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
 #define TBX_SI_DIRECT_MIN_CTAS 3
 #define TBX_E_SPRITE_PATCH 1u
 #define TBX_E_DIGIT_PATCH 2u
+#ifdef TBX_SI_STATS
+__device__ unsigned long long d_si_stats[48];
+#endif
 
 template <int TX, int TY>
 __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ TbxAreaPlan plan_c,
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
         }
         const int e = n + __popc(m & lt_mask);
         ent[2 * e] = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), (int)((uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16)), (int)(gray | (kind << 8) | (ref << 16)));
-        ent[2 * e + 1] = make_int4((int)((uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24)), fx0 | (fx1 << 8) | (fy0 << 16) | (fy1 << 24), 0, 0);
+        ent[2 * e + 1] = make_int4((int)((uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24)), fx0 | (fx1 << 8) | (fy0 << 16) | (fy1 << 24), 0, slot);
       }
       n += __popc(m);
     }
@@ -468,6 +471,19 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       total += __reduce_add_sync(0xffffffffu, (e < n && !patch) ? area : 0);
       any_shared |= __any_sync(0xffffffffu, shared);
     }
+#ifdef TBX_SI_STATS
+    { /* tuning build: what the evaluated pixels are made of */
+      if (lane == 0) { atomicAdd(&d_si_stats[0], 1ull); atomicAdd(&d_si_stats[1], (unsigned long long)n); atomicAdd(&d_si_stats[3], (unsigned long long)n_eval);
+                       atomicAdd(&d_si_stats[4], (unsigned long long)total); atomicAdd(&d_si_stats[7], (unsigned long long)((total + 31) / 32)); }
+      for (int k = lane; k < n_eval; k += 32) {
+        const int id = lst[k] & 0xffff, conf = lst[k] >> 16, slot = ent[2 * id + 1].w;
+        const int cls = slot < SI_SLOT_LIVES ? 0 : slot < SI_SLOT_SHIELDS ? 1 : slot < SI_SLOT_ENEMIES ? 2 : slot < SI_SLOT_SHIP ? 3 : slot == SI_SLOT_SHIP ? 4 : slot == SI_SLOT_UFO ? 5 : 6;
+        atomicAdd(&d_si_stats[16 + cls], 1ull); atomicAdd(&d_si_stats[24 + cls], (unsigned long long)lcnt[k]);
+        if (conf) { atomicAdd(&d_si_stats[5], 1ull); atomicAdd(&d_si_stats[6], (unsigned long long)lcnt[k]); atomicAdd(&d_si_stats[32 + cls], 1ull); }
+      }
+      for (int e = lane; e < n; e += 32) if (ent[2 * e + 1].z) atomicAdd(&d_si_stats[2], 1ull);
+    }
+#endif
     /* the base copy must have landed before anything is written over it */
     if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
