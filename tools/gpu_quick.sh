@@ -1,11 +1,8 @@
 #!/bin/bash
-# quick single-GPU check: headline line with the driver's flags and the default, plus ncu captures of the SI / Amidar direct kernels (reps kept)
+# quick single-GPU check
 set -x
 mkdir -p gpurun_out
 B="--no-cpu-baseline --no-e2e --no-protocol --no-states"
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/q_bench_k20.log 2>&1; tail -1 gpurun_out/q_bench_k20.log | cut -c1-300
-timeout 600 python bench.py $B > gpurun_out/q_bench_k200.log 2>&1; tail -1 gpurun_out/q_bench_k200.log | cut -c1-300
-for g in space_invaders amidar; do
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:_direct -s 6 -c 1 -o gpurun_out/q_prof_$g python bench.py --game $g --steps 4 --warmup 3 $B > gpurun_out/q_ncu_$g.log 2>&1
-  ls -la gpurun_out/q_prof_$g.ncu-rep
-done
+TBX_LIB_PATH=$PWD/toybox_b200/libtoybox_b200_stats.so timeout 300 python tools/si_stats.py 2000 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_gpu_area_kernels.py tests/test_gpu_parity.py -m gpu -q -x -k "amidar or Amidar or corridor or mixed" > gpurun_out/q_pytest.log 2>&1; tail -3 gpurun_out/q_pytest.log
+timeout 300 python bench.py --game amidar --steps 50 --warmup 5 $B > gpurun_out/q_bench_amidar.log 2>&1; tail -1 gpurun_out/q_bench_amidar.log | cut -c1-900

@@ -787,6 +787,20 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
       mrec[3 * lane + 2] = make_int4(ncol * nrow, ncol > 1 ? (int)__ldg(&A.inv32[ncol]) : 0, 0, 0);
     }
     __syncwarp();
+    /* which movers can reach the source windows of mover `lane`'s pixels (itself, and whoever walks next to it): a pixel paints those only */
+    if (lane < AMI_N_MOVERS) {
+      uint32_t near = 0;
+      if (valid) {
+        const int sx0 = __ldg(&plan->xs0[fx0]), sx1 = __ldg(&plan->xs0[fx1]) + TX, sy0 = __ldg(&plan->ys0[fy0]), sy1 = __ldg(&plan->ys0[fy1]) + TY;
+#pragma unroll
+        for (int m = 0; m < AMI_N_MOVERS; m++) {
+          const int4 rc = mrec[3 * m];
+          if (((vm >> m) & 1u) && rc.x < sx1 && rc.z > sx0 && rc.y < sy1 && rc.w > sy0) near |= 1u << m;
+        }
+      }
+      mrec[3 * lane + 2].z = (int)near;
+    }
+    __syncwarp();
     int total = 0;
 #pragma unroll
     for (int m = 0; m < AMI_N_MOVERS; m++) total += mrec[3 * m + 2].x;
@@ -826,7 +840,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
         }
         lo[k] = row;
       }
-      uint32_t mleft = vm;
+      uint32_t mleft = (uint32_t)mrec[3 * mym + 2].z;
       while (mleft) { /* draw order: enemies, then the player */
         const int m = __ffs(mleft) - 1;
         mleft &= mleft - 1;
