@@ -13,6 +13,6 @@ out = (C.c_ulonglong * 48)()
 pool.render(); L.tbx_debug_si_stats(out, 1)
 pool.render(); L.tbx_debug_si_stats(out, 1)
 v = np.array(out[:], dtype=np.float64); e = v[0]
-print("envs", e, "entries/env %.1f patched %.1f evaluated %.1f (conf %.2f)  pixels/env %.1f (conf %.1f)  batches/env %.2f" % (v[1]/e, v[2]/e, v[3]/e, v[5]/e, v[4]/e, v[6]/e, v[7]/e))
+print("envs", e, "entries/env %.1f patched %.1f evaluated %.1f (conf %.2f)  pixels/env %.1f (conf %.1f)  batches/env %.2f  row-lut entries/env %.2f pixels/env %.1f" % (v[1]/e, v[2]/e, v[3]/e, v[5]/e, v[4]/e, v[6]/e, v[7]/e, v[8]/e, v[9]/e))
 for i, name in enumerate(["score digits", "lives digits", "shields", "enemies", "ship", "ufo", "lasers"]):
     print("  %-13s entries/env %.2f  pixels/env %.1f  conf entries/env %.2f" % (name, v[16+i]/e, v[24+i]/e, v[32+i]/e))
