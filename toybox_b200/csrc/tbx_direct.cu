@@ -49,6 +49,7 @@ void tbx_direct_geometry(int game, int out_w, int out_h, DirectArgs &d) {
   d.hstride = (out_w + 3) & ~3;
   d.smem_base = align16(out_w * out_h);
   if (game == TBX_BREAKOUT) {
+    d.smem_base += TBX_BRK_TAB_BYTES; /* the kernel's small tables follow the staged frame */
     /* per warp: its env's record, the wall's H rows, the movers' records; two record stages */
     d.warp_bytes = align16(TBX_WORDS(BrkRec) * 4) + align16(TBX_BRK_MAX_ROWS * d.hstride * (int)sizeof(float)) + 256;
     d.smem_total = d.smem_base + 2 * TBX_WORDS(BrkRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;

@@ -27,6 +27,7 @@ struct TbxMover { int x0, y0, x1, y1; uint32_t gray; };
 
 /* ------------------------------------------------------------------ Breakout */
 #define TBX_BD_MAX_STATIC 16
+#define TBX_BD_MAX_CLS 8
 #define BRK_N_MOVERS (1 + TBX_BRK_MAX_BALLS) /* paddle, balls in draw order */
 typedef struct TbxBrkDirect {
   int32_t ok;                    /* 0: this (config, output size) pair is rendered by the tile kernel */
@@ -46,6 +47,11 @@ typedef struct TbxBrkDirect {
   uint32_t inv32[TBX_AREA_MAX_DST + 1]; /* ceil(2^32 / n) for n >= 2: i / n == umulhi(i, inv32[n]) for the small i used here */
   alignas(16) float hlut[TBX_BRK_MAX_ROWS][4][TBX_AREA_MAX_DST];  /* [brick row][alive(col0) | alive(col0 + 1) << 1][dx] */
   alignas(16) float hstatic[TBX_BD_MAX_STATIC][TBX_AREA_MAX_DST]; /* horizontal sums of the base-frame-0 rows around the wall */
+  /* base frame 0 by row classes: its rows fall into a few classes of identical rows (background, borders, HUD band), so the
+   * movers' source windows read a 2 KB table in shared memory instead of the 38 KB frame.  n_cls == 0: more classes than fit */
+  int32_t n_cls, _pad2[3];
+  uint8_t rowcls[TBX_BRK_H];
+  alignas(16) uint8_t clsrows[TBX_BD_MAX_CLS * TBX_BRK_W + 16];
 } TbxBrkDirect;
 
 /* paddle (m == 0) or ball m - 1 as a clipped rectangle */

@@ -1044,6 +1044,19 @@ void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, c
     A.hud_dyhi = y1 > 0 ? pl.ydhi[y1 - 1] : -1;
     if (A.wdy0 <= A.hud_dyhi) return;
   }
+  /* rows of base frame 0 by class */
+  A.n_cls = 0;
+  for (int y = 0; y < H; y++) {
+    int cls = -1;
+    for (int k = 0; k < A.n_cls && cls < 0; k++)
+      if (memcmp(A.clsrows + (size_t)k * W, base0 + (size_t)y * W, W) == 0) cls = k;
+    if (cls < 0) {
+      if (A.n_cls == TBX_BD_MAX_CLS) { A.n_cls = 0; break; }
+      cls = A.n_cls++;
+      memcpy(A.clsrows + (size_t)cls * W, base0 + (size_t)y * W, W);
+    }
+    A.rowcls[y] = (uint8_t)cls;
+  }
   A.ok = 1;
 }
 

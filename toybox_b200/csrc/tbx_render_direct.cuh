@@ -23,6 +23,8 @@
 namespace tbxk {
 
 #define TBX_DIRECT_THREADS 256
+#define TBX_BRK_DIG_BYTES (2 * TBX_MAX_DIGITS * 10 * 24)
+#define TBX_BRK_TAB_BYTES (TBX_BRK_DIG_BYTES + TBX_BD_MAX_CLS * TBX_BRK_W + 16 + TBX_BRK_H + (TBX_AREA_MAX_DST + 1 + 3) / 4 * 16)
 #ifndef TBX_DIRECT_MIN_CTAS
 #define TBX_DIRECT_MIN_CTAS 4
 #endif
@@ -46,6 +48,14 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   extern __shared__ uint4 smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(smem_raw);
   uint8_t *sbase = smem;                                                        /* base frame 1, down-sampled */
+  /* small hot tables, copied once per CTA (TBX_BRK_TAB_BYTES after the frame): the reads they replace were the kernel's main
+   * long-scoreboard stalls (L1 misses on sparse global tables) */
+  uint8_t *tab = smem + ((plan_c.dw * plan_c.dh + 15) & ~15);
+  uint32_t *sdig = reinterpret_cast<uint32_t *>(tab);                           /* [20 slots x 10 digits][6 words]: header + up to 20 pixels */
+  uint8_t *scls = tab + TBX_BRK_DIG_BYTES;                                      /* base frame 0 by row classes */
+  uint8_t *srowcls = scls + TBX_BD_MAX_CLS * TBX_BRK_W + 16;
+  uint32_t *sinv = reinterpret_cast<uint32_t *>(srowcls + TBX_BRK_H);           /* inv32[] */
+  __shared__ int s_bigdig;
   uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2][RW][8 envs] */
   const TbxBrkDirect *__restrict__ Ap = reinterpret_cast<const TbxBrkDirect *>(d.aux);
   const TbxBrkDirect &A = *Ap;
@@ -72,12 +82,29 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   if (tid == 0) s_next[0] = (int)gridDim.x + atomicAdd(d.sched, 1);
   if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
+  const TbxDigitPatch *__restrict__ gpatches = a.patches[1];
+  if (tid == 0) s_bigdig = gpatches ? 0 : 1;
+  __syncthreads();
+  if (gpatches)
+    for (int e = tid; e < 2 * TBX_MAX_DIGITS * 10; e += TBX_DIRECT_THREADS) {
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(gpatches + e);
+      const uint32_t hdr = __ldg(src);
+      if (((hdr >> 16) & 255u) * (hdr >> 24) > 20u) atomicOr(&s_bigdig, 1);
+#pragma unroll
+      for (int w = 0; w < 6; w++) sdig[e * 6 + w] = __ldg(src + w);
+    }
+  const int n_cls = A.n_cls;
+  for (int i = tid; i < (n_cls * TBX_BRK_W + 16) / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(scls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.clsrows) + i);
+  for (int i = tid; i < TBX_BRK_H / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(srowcls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.rowcls) + i);
+  for (int i = tid; i <= TBX_AREA_MAX_DST; i += TBX_DIRECT_THREADS) sinv[i] = __ldg(&A.inv32[i]);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk copies below read sbase through the async proxy */
 
   const int ok = A.ok, ncols = A.ncols, nrows = A.nrows, wdy0 = A.wdy0, wdy1 = A.wdy1, hud_dyhi = A.hud_dyhi;
   const int wy0 = A.wy0, wy1 = A.wy0 + A.nrows * A.bh;
   const uint32_t paddle_gray = A.paddle_gray, ball_gray = A.ball_gray;
   const TbxDigitPatch *__restrict__ patches = a.patches[1];
+  __syncthreads(); /* the tables are complete */
+  const bool dig_smem = s_bigdig == 0;
   const uint32_t *R = recw;
 
   int st = 0, it = 0, nxt = 0;
@@ -107,7 +134,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
     if (lane < 2 * TBX_MAX_DIGITS && patches) {
       const int field = lane >= TBX_MAX_DIGITS;
       dig = tbx_digit_at((int32_t)R[field ? TBX_HW(lives) : TBX_HW(score)], lane - field * TBX_MAX_DIGITS);
-      if (dig >= 0) { P = patches + lane * 10 + dig; bad |= __ldg(&P->w) == 0; }
+      if (dig >= 0) { P = patches + lane * 10 + dig; bad |= (dig_smem ? (sdig[(lane * 10 + dig) * 6] >> 16) & 255u : (uint32_t)__ldg(&P->w)) == 0; }
     }
     const bool covered = ok && patches && (int32_t)R[TBX_HW(tbl)] == cfg_c.default_tbl;
     if (!covered || __any_sync(0xffffffffu, bad)) { /* the general kernel's */
@@ -134,7 +161,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
       const int ncol = valid ? fx1 - fx0 + 1 : 0, nrow = valid ? fy1 - fy0 + 1 : 0;
       mrec[3 * lane + 0] = make_int4(mine.x0, mine.y0, mine.x1, mine.y1);
       mrec[3 * lane + 1] = make_int4((int)mine.gray * 0x01010101, fx0, fy0, ncol);
-      mrec[3 * lane + 2] = make_int4(ncol * nrow, ncol > 1 ? (int)__ldg(&A.inv32[ncol]) : 0, 0, 0);
+      mrec[3 * lane + 2] = make_int4(ncol * nrow, ncol > 1 ? (int)sinv[ncol] : 0, 0, 0);
     }
     __syncwarp();
     int total = 0;
@@ -164,11 +191,12 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
 #pragma unroll
       for (int k = 0; k < TY; k++) {
         const int y = min(ys + k, TBX_BRK_H - 1); /* surplus taps carry zero weights: any in-frame pixel will do */
-        const int ob = y * TBX_BRK_W + xs;
-        const uint32_t w0 = __ldg(base0w + (ob >> 2)), w1 = __ldg(base0w + (ob >> 2) + 1); /* the frame buffer has 16 bytes of slack */
-        lo[k] = __funnelshift_r(w0, w1, 8 * (ob & 3));
+        /* the row of base frame 0: from its class in shared memory, or from the frame (both have 16 bytes of slack) */
+        const uint32_t *rowp = n_cls ? reinterpret_cast<const uint32_t *>(scls + (int)srowcls[y] * TBX_BRK_W) : base0w + y * (TBX_BRK_W / 4);
+        const uint32_t w0 = rowp[xs >> 2], w1 = rowp[(xs >> 2) + 1];
+        lo[k] = __funnelshift_r(w0, w1, 8 * (xs & 3));
         hi[k] = 0;
-        if (TX > 4) { const uint32_t w2 = __ldg(base0w + (ob >> 2) + 2); hi[k] = __funnelshift_r(w1, w2, 8 * (ob & 3)) & 255u; }
+        if (TX > 4) { const uint32_t w2 = rowp[(xs >> 2) + 2]; hi[k] = __funnelshift_r(w1, w2, 8 * (xs & 3)) & 255u; }
       }
       if (__any_sync(0xffffffffu, act && ys < wy1 && ys + TY > wy0)) { /* the brick grid */
         uint32_t cb[TX];
@@ -289,11 +317,14 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
       while (dm) {
         const int l = __ffs(dm) - 1;
         dm &= dm - 1;
-        const TbxDigitPatch *Q = reinterpret_cast<const TbxDigitPatch *>(__shfl_sync(0xffffffffu, (unsigned long long)P, l));
-        const int px0 = __ldg(&Q->x0), py0 = __ldg(&Q->y0), pw = __ldg(&Q->w), ph = __ldg(&Q->h);
+        const int dgt = __shfl_sync(0xffffffffu, dig, l);
+        /* the patch: header word (x0, y0, w, h), then w x h pixels -- the compact copy in shared memory, or the table itself */
+        const uint8_t *Q = dig_smem ? reinterpret_cast<const uint8_t *>(sdig + (l * 10 + dgt) * 6) : reinterpret_cast<const uint8_t *>(patches + l * 10 + dgt);
+        const uint32_t hdr = *reinterpret_cast<const uint32_t *>(Q);
+        const int px0 = hdr & 255u, py0 = (hdr >> 8) & 255u, pw = (hdr >> 16) & 255u, ph = hdr >> 24;
         const int cc = lane & 7;
         if (cc < pw)
-          for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = __ldg(&Q->px[r * pw + cc]);
+          for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = Q[4 + r * pw + cc];
       }
     }
     __syncwarp(); /* the movers' pixels go over the wall's */
