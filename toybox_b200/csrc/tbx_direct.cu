@@ -45,13 +45,15 @@ cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, 
   return cudaSuccess;
 }
 
-void tbx_direct_geometry(int game, int out_w, int out_h, DirectArgs &d) {
+void tbx_direct_geometry(int game, int out_w, int out_h, int brk_rows, DirectArgs &d) {
   d.hstride = (out_w + 3) & ~3;
   d.smem_base = align16(out_w * out_h);
   if (game == TBX_BREAKOUT) {
-    d.smem_base += TBX_BRK_TAB_BYTES; /* the kernel's small tables follow the staged frame */
+    if (brk_rows < 1 || brk_rows > TBX_BRK_MAX_ROWS) brk_rows = TBX_BRK_MAX_ROWS;
+    /* the kernel's small tables follow the staged frame: digit patches, base-frame row classes, division table, the wall's H look-up */
+    d.smem_base += TBX_BRK_TAB_BYTES + align16(brk_rows * 4 * d.hstride * (int)sizeof(float));
     /* per warp: its env's record, the wall's H rows, the movers' records; two record stages */
-    d.warp_bytes = align16(TBX_WORDS(BrkRec) * 4) + align16(TBX_BRK_MAX_ROWS * d.hstride * (int)sizeof(float)) + 256;
+    d.warp_bytes = align16(TBX_WORDS(BrkRec) * 4) + align16(brk_rows * d.hstride * (int)sizeof(float)) + 256;
     d.smem_total = d.smem_base + 2 * TBX_WORDS(BrkRec) * TBX_EPC * 4 + (TBX_DIRECT_THREADS / 32) * d.warp_bytes;
   } else if (game == TBX_AMIDAR) {
     /* per warp: its env's record, the tile rows as looks, the movers' records; two record stages */

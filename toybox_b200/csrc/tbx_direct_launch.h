@@ -23,7 +23,7 @@ struct DirectArgs {
 cudaError_t tbx_direct_build(const tbx::Config &c, const BrkTable *brk_default, const tbx::ResizeTab &rs, const TbxAreaPlan &plan, const uint8_t *base0_gray,
                              void **d_aux, void **d_aux2);
 /* shared memory per warp / floats per H row for an output width */
-void tbx_direct_geometry(int game, int out_w, int out_h, tbxk::DirectArgs &d);
+void tbx_direct_geometry(int game, int out_w, int out_h, int brk_rows, tbxk::DirectArgs &d); /* brk_rows: Breakout's brick rows (config) */
 /* direct INTER_AREA kernel instantiated for at least tx x ty taps (tx <= 5, ty <= 4) */
 cudaError_t tbx_launch_direct(int game, int tx, int ty, const tbxk::RenderArgs &a, const void *cfg_host, const TbxAreaPlan &plan, const tbxk::DirectArgs &d,
                               cudaStream_t s);

@@ -533,7 +533,7 @@ static int render_impl(tbx_pool *p, uint8_t *dst, int mode, int out_w, int out_h
           if (!p->d_fb) { CK(cudaMalloc(&p->d_fb, ((size_t)p->n_pad + 8) * sizeof(int32_t))); CK(cudaMemsetAsync(p->d_fb, 0, 8 * sizeof(int32_t), s)); }
           DirectArgs da;
           da.aux = ar->d_direct; da.aux2 = ar->d_direct2; da.fb_list = p->d_fb + 8; da.fb_count = p->d_fb; da.sched = p->d_fb + 2;
-          tbx_direct_geometry(p->game, out_w, out_h, da);
+          tbx_direct_geometry(p->game, out_w, out_h, p->game == TBX_BREAKOUT ? p->cfg.brk.n_rows : 0, da);
           CK(tbx_launch_direct(p->game, tx, ty, a, cfg_ptr(p), ar->plan, da, s));
           if (p->game == TBX_SPACE_INVADERS) return TBX_OK; /* covers every env: nothing is handed over */
           a.env_list = p->d_fb + 8;

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   uint8_t *scls = tab + TBX_BRK_DIG_BYTES;                                      /* base frame 0 by row classes */
   uint8_t *srowcls = scls + TBX_BD_MAX_CLS * TBX_BRK_W + 16;
   uint32_t *sinv = reinterpret_cast<uint32_t *>(srowcls + TBX_BRK_H);           /* inv32[] */
+  float *shlut = reinterpret_cast<float *>(tab + TBX_BRK_TAB_BYTES);            /* [brick row][2 alive bits][hstride]: the wall's H look-up */
   __shared__ int s_bigdig;
   uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2][RW][8 envs] */
   const TbxBrkDirect *__restrict__ Ap = reinterpret_cast<const TbxBrkDirect *>(d.aux);
@@ -97,6 +98,10 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   for (int i = tid; i < (n_cls * TBX_BRK_W + 16) / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(scls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.clsrows) + i);
   for (int i = tid; i < TBX_BRK_H / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(srowcls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.rowcls) + i);
   for (int i = tid; i <= TBX_AREA_MAX_DST; i += TBX_DIRECT_THREADS) sinv[i] = __ldg(&A.inv32[i]);
+  for (int i = tid; i < A.nrows * 4 * (plan_c.dw >> 2); i += TBX_DIRECT_THREADS) { /* float4 pieces of the rows in use */
+    const int rp = i / (plan_c.dw >> 2), c4 = i - rp * (plan_c.dw >> 2);
+    *reinterpret_cast<float4 *>(shlut + rp * d.hstride + 4 * c4) = __ldg(reinterpret_cast<const float4 *>(&A.hlut[rp >> 2][rp & 3][4 * c4]));
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk copies below read sbase through the async proxy */
 
   const int ok = A.ok, ncols = A.ncols, nrows = A.nrows, wdy0 = A.wdy0, wdy1 = A.wdy1, hud_dyhi = A.hud_dyhi;
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
           const int c0 = __ldg(&A.col0[dx]);
 #pragma unroll
           for (int r = 0; r < TBX_BRK_MAX_ROWS; r++)
-            if (r < nrows) hw[r * hs + dx] = __ldg(&A.hlut[r][(rowmask[r] >> c0) & 3u][dx]);
+            if (r < nrows) hw[r * hs + dx] = shlut[(r * 4 + ((rowmask[r] >> c0) & 3u)) * hs + dx];
         }
         __syncwarp();
         TBX_DIRECT_LAND();
@@ -318,13 +323,20 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
         const int l = __ffs(dm) - 1;
         dm &= dm - 1;
         const int dgt = __shfl_sync(0xffffffffu, dig, l);
-        /* the patch: header word (x0, y0, w, h), then w x h pixels -- the compact copy in shared memory, or the table itself */
-        const uint8_t *Q = dig_smem ? reinterpret_cast<const uint8_t *>(sdig + (l * 10 + dgt) * 6) : reinterpret_cast<const uint8_t *>(patches + l * 10 + dgt);
-        const uint32_t hdr = *reinterpret_cast<const uint32_t *>(Q);
-        const int px0 = hdr & 255u, py0 = (hdr >> 8) & 255u, pw = (hdr >> 16) & 255u, ph = hdr >> 24;
         const int cc = lane & 7;
-        if (cc < pw)
-          for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = Q[4 + r * pw + cc];
+        /* the patch: header word (x0, y0, w, h), then w x h pixels -- the compact copy in shared memory, or the table itself */
+        if (dig_smem) {
+          const uint8_t *Q = reinterpret_cast<const uint8_t *>(sdig + (l * 10 + dgt) * 6);
+          const uint32_t hdr = *reinterpret_cast<const uint32_t *>(Q);
+          const int px0 = hdr & 255u, py0 = (hdr >> 8) & 255u, pw = (hdr >> 16) & 255u, ph = hdr >> 24;
+          if (cc < pw)
+            for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = Q[4 + r * pw + cc];
+        } else {
+          const TbxDigitPatch *Q = patches + l * 10 + dgt;
+          const int px0 = __ldg(&Q->x0), py0 = __ldg(&Q->y0), pw = __ldg(&Q->w), ph = __ldg(&Q->h);
+          if (cc < pw)
+            for (int r = lane >> 3; r < ph; r += 4) out[(py0 + r) * dw + px0 + cc] = __ldg(&Q->px[r * pw + cc]);
+        }
       }
     }
     __syncwarp(); /* the movers' pixels go over the wall's */
