@@ -23,7 +23,10 @@
 namespace tbxk {
 
 #define TBX_DIRECT_THREADS 256
-#define TBX_BRK_DIG_BYTES (2 * TBX_MAX_DIGITS * 10 * 24)
+#define TBX_BRK_DIG_SLOTS 6  /* digit slots whose patches are kept in shared memory: score digits 0..3, lives digits 0..1 */
+#define TBX_BRK_DIG_WORDS 13 /* header word + up to 48 pixels */
+#define TBX_BRK_DIG_BYTES (TBX_BRK_DIG_SLOTS * 10 * TBX_BRK_DIG_WORDS * 4)
+__device__ __forceinline__ int brk_dig_cid(int slot) { return slot < 4 ? slot : slot >= TBX_MAX_DIGITS && slot < TBX_MAX_DIGITS + 2 ? slot - TBX_MAX_DIGITS + 4 : -1; }
 #define TBX_BRK_TAB_BYTES (TBX_BRK_DIG_BYTES + TBX_BD_MAX_CLS * TBX_BRK_W + 16 + TBX_BRK_H + (TBX_AREA_MAX_DST + 1 + 3) / 4 * 16)
 #ifndef TBX_DIRECT_MIN_CTAS
 #define TBX_DIRECT_MIN_CTAS 4
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   /* small hot tables, copied once per CTA (TBX_BRK_TAB_BYTES after the frame): the reads they replace were the kernel's main
    * long-scoreboard stalls (L1 misses on sparse global tables) */
   uint8_t *tab = smem + ((plan_c.dw * plan_c.dh + 15) & ~15);
-  uint32_t *sdig = reinterpret_cast<uint32_t *>(tab);                           /* [20 slots x 10 digits][6 words]: header + up to 20 pixels */
+  uint32_t *sdig = reinterpret_cast<uint32_t *>(tab);                           /* [6 slots x 10 digits][13 words]: header + up to 48 pixels */
   uint8_t *scls = tab + TBX_BRK_DIG_BYTES;                                      /* base frame 0 by row classes */
   uint8_t *srowcls = scls + TBX_BD_MAX_CLS * TBX_BRK_W + 16;
   uint32_t *sinv = reinterpret_cast<uint32_t *>(srowcls + TBX_BRK_H);           /* inv32[] */
@@ -86,13 +89,13 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   const TbxDigitPatch *__restrict__ gpatches = a.patches[1];
   if (tid == 0) s_bigdig = gpatches ? 0 : 1;
   __syncthreads();
-  if (gpatches)
-    for (int e = tid; e < 2 * TBX_MAX_DIGITS * 10; e += TBX_DIRECT_THREADS) {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(gpatches + e);
-      const uint32_t hdr = __ldg(src);
-      if (((hdr >> 16) & 255u) * (hdr >> 24) > 20u) atomicOr(&s_bigdig, 1);
-#pragma unroll
-      for (int w = 0; w < 6; w++) sdig[e * 6 + w] = __ldg(src + w);
+  if (gpatches) /* the slots that are in use in practice: the score's low 4 digits, the lives' low 2 (the others read the table itself) */
+    for (int i = tid; i < TBX_BRK_DIG_SLOTS * 10 * TBX_BRK_DIG_WORDS; i += TBX_DIRECT_THREADS) {
+      const int e = i / TBX_BRK_DIG_WORDS, w = i - e * TBX_BRK_DIG_WORDS, cid = e / 10, slot = cid < 4 ? cid : cid + TBX_MAX_DIGITS - 4;
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(gpatches + slot * 10 + (e - cid * 10));
+      const uint32_t v = __ldg(src + w);
+      if (w == 0 && ((v >> 16) & 255u) * (v >> 24) > 4u * (TBX_BRK_DIG_WORDS - 1)) atomicOr(&s_bigdig, 1);
+      sdig[i] = v;
     }
   const int n_cls = A.n_cls;
   for (int i = tid; i < (n_cls * TBX_BRK_W + 16) / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(scls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.clsrows) + i);
@@ -139,7 +142,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
     if (lane < 2 * TBX_MAX_DIGITS && patches) {
       const int field = lane >= TBX_MAX_DIGITS;
       dig = tbx_digit_at((int32_t)R[field ? TBX_HW(lives) : TBX_HW(score)], lane - field * TBX_MAX_DIGITS);
-      if (dig >= 0) { P = patches + lane * 10 + dig; bad |= (dig_smem ? (sdig[(lane * 10 + dig) * 6] >> 16) & 255u : (uint32_t)__ldg(&P->w)) == 0; }
+      if (dig >= 0) {
+        const int cid = brk_dig_cid(lane);
+        P = patches + lane * 10 + dig;
+        bad |= (dig_smem && cid >= 0 ? (sdig[(cid * 10 + dig) * TBX_BRK_DIG_WORDS] >> 16) & 255u : (uint32_t)__ldg(&P->w)) == 0;
+      }
     }
     const bool covered = ok && patches && (int32_t)R[TBX_HW(tbl)] == cfg_c.default_tbl;
     if (!covered || __any_sync(0xffffffffu, bad)) { /* the general kernel's */
@@ -325,8 +332,9 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
         const int dgt = __shfl_sync(0xffffffffu, dig, l);
         const int cc = lane & 7;
         /* the patch: header word (x0, y0, w, h), then w x h pixels -- the compact copy in shared memory, or the table itself */
-        if (dig_smem) {
-          const uint8_t *Q = reinterpret_cast<const uint8_t *>(sdig + (l * 10 + dgt) * 6);
+        const int cid = brk_dig_cid(l);
+        if (dig_smem && cid >= 0) {
+          const uint8_t *Q = reinterpret_cast<const uint8_t *>(sdig + (cid * 10 + dgt) * TBX_BRK_DIG_WORDS);
           const uint32_t hdr = *reinterpret_cast<const uint32_t *>(Q);
           const int px0 = hdr & 255u, py0 = (hdr >> 8) & 255u, pw = (hdr >> 16) & 255u, ph = hdr >> 24;
           if (cc < pw)
