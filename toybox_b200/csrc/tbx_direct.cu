@@ -1,5 +1,6 @@
 /* tbx_direct.cu -- host side of the direct INTER_AREA kernels (tbx_render_direct.cuh): table upload and launchers.  A
  * translation unit of its own so that it compiles in parallel with, and rebuilds independently of, tbx_pool.cu. */
+#include <mutex>
 #include "tbx_render_direct.cuh"
 #include <stdlib.h>
 #include <vector>
@@ -67,20 +68,31 @@ void tbx_direct_geometry(int game, int out_w, int out_h, int brk_rows, DirectArg
   }
 }
 
-/* persistent grid: as many CTAs as the device keeps resident (cached per device and kernel), each walks its share of the chunks */
+/* persistent grid: as many CTAs as the device keeps resident, each walks its share of the chunks.  The residency is cached per
+ * (kernel, shared memory, device): the kernels share function-pointer types, so the cache is keyed by the pointer's value */
 template <class K> static cudaError_t persistent_grid(K kernel, int smem, int n_chunks, int *grid_out) {
-  static int resident[64] = {0};
+  struct Entry { const void *k; int smem, dev, resident; };
+  static Entry cache[64];
+  static int n_cache = 0;
+  static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!resident[dev]) {
+  int resident = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_cache; i++)
+      if (cache[i].k == (const void *)kernel && cache[i].smem == smem && cache[i].dev == dev) resident = cache[i].resident;
+  }
+  if (!resident) {
     int per_sm = 0, sms = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TBX_DIRECT_THREADS, smem);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    resident[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    std::lock_guard<std::mutex> lock(mu);
+    if (n_cache < 64) cache[n_cache++] = Entry{(const void *)kernel, smem, dev, resident};
   }
-  int grid = n_chunks < resident[dev] ? n_chunks : resident[dev];
+  int grid = n_chunks < resident ? n_chunks : resident;
   if (const char *env = getenv("TBX_DIRECT_GRID")) if (atoi(env) > 0) grid = atoi(env) < n_chunks ? atoi(env) : n_chunks; /* tuning / tests */
   *grid_out = grid;
   return cudaSuccess;
@@ -88,12 +100,13 @@ template <class K> static cudaError_t persistent_grid(K kernel, int smem, int n_
 
 template <int TX, int TY> static cudaError_t launch_brk(const RenderArgs &a, const BrkCfg &cfg, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
   /* the attribute is per device: set it on every launch (a cheap host-side call) rather than caching it per process */
-  cudaError_t e = cudaFuncSetAttribute(brk_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
+  const int smem = d.smem_total + brk_plan_smem_bytes(TX, TY, plan.dw, plan.dh); /* the plan's per-pixel tables go behind the rest */
+  cudaError_t e = cudaFuncSetAttribute(brk_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int grid = 1;
-  e = persistent_grid(brk_direct_kernel<TX, TY>, d.smem_total, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
+  e = persistent_grid(brk_direct_kernel<TX, TY>, smem, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
   if (e != cudaSuccess) return e;
-  brk_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, d.smem_total, s>>>(a, cfg, plan, d);
+  brk_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, smem, s>>>(a, cfg, plan, d);
   return cudaGetLastError();
 }
 template <int TX, int TY> static cudaError_t launch_si(const RenderArgs &a, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {

@@ -26,6 +26,9 @@ namespace tbxk {
 #define TBX_BRK_DIG_SLOTS 6  /* digit slots whose patches are kept in shared memory: score digits 0..3, lives digits 0..1 */
 #define TBX_BRK_DIG_WORDS 13 /* header word + up to 48 pixels */
 #define TBX_BRK_DIG_BYTES (TBX_BRK_DIG_SLOTS * 10 * TBX_BRK_DIG_WORDS * 4)
+/* pitch / bytes of the plan tables the Breakout kernel keeps behind its other shared memory */
+__host__ __device__ __forceinline__ int brk_plan_pitch(int dw, int dh) { return ((dw > dh ? dw : dh) + 3) & ~3; }
+__host__ __device__ __forceinline__ int brk_plan_smem_bytes(int tx, int ty, int dw, int dh) { return ((tx + ty) * brk_plan_pitch(dw, dh) * 4 + 2 * brk_plan_pitch(dw, dh) * 2 + 15) & ~15; }
 __device__ __forceinline__ int brk_dig_cid(int slot) { return slot < 4 ? slot : slot >= TBX_MAX_DIGITS && slot < TBX_MAX_DIGITS + 2 ? slot - TBX_MAX_DIGITS + 4 : -1; }
 #define TBX_BRK_TAB_BYTES (TBX_BRK_DIG_BYTES + TBX_BD_MAX_CLS * TBX_BRK_W + 16 + TBX_BRK_H + (TBX_AREA_MAX_DST + 1 + 3) / 4 * 16)
 #ifndef TBX_DIRECT_MIN_CTAS
@@ -59,6 +62,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   uint8_t *srowcls = scls + TBX_BD_MAX_CLS * TBX_BRK_W + 16;
   uint32_t *sinv = reinterpret_cast<uint32_t *>(srowcls + TBX_BRK_H);           /* inv32[] */
   float *shlut = reinterpret_cast<float *>(tab + TBX_BRK_TAB_BYTES);            /* [brick row][2 alive bits][hstride]: the wall's H look-up */
+  /* the resize plan's per-pixel tables, behind everything else (brk_plan_smem_bytes: the launch adds them to d.smem_total) */
+  const int ps = brk_plan_pitch(plan_c.dw, plan_c.dh);
+  float *sxa = reinterpret_cast<float *>(smem + d.smem_total);                  /* [TX][ps] */
+  float *sya = sxa + TX * ps;                                                   /* [TY][ps] */
+  uint16_t *sxs = reinterpret_cast<uint16_t *>(sya + TY * ps), *sys = sxs + ps; /* xs0, ys0 */
   __shared__ int s_bigdig;
   uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2][RW][8 envs] */
   const TbxBrkDirect *__restrict__ Ap = reinterpret_cast<const TbxBrkDirect *>(d.aux);
@@ -101,6 +109,14 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   for (int i = tid; i < (n_cls * TBX_BRK_W + 16) / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(scls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.clsrows) + i);
   for (int i = tid; i < TBX_BRK_H / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(srowcls)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.rowcls) + i);
   for (int i = tid; i <= TBX_AREA_MAX_DST; i += TBX_DIRECT_THREADS) sinv[i] = __ldg(&A.inv32[i]);
+  for (int i = tid; i < ps; i += TBX_DIRECT_THREADS) {
+    const int jx = min(i, plan_c.dw - 1), jy = min(i, plan_c.dh - 1);
+#pragma unroll
+    for (int t = 0; t < TX; t++) sxa[t * ps + i] = __ldg(&a.plan->xalpha[t][jx]);
+#pragma unroll
+    for (int t = 0; t < TY; t++) sya[t * ps + i] = __ldg(&a.plan->yalpha[t][jy]);
+    sxs[i] = __ldg(&a.plan->xs0[jx]); sys[i] = __ldg(&a.plan->ys0[jy]);
+  }
   for (int i = tid; i < A.nrows * 4 * (plan_c.dw >> 2); i += TBX_DIRECT_THREADS) { /* float4 pieces of the rows in use */
     const int rp = i / (plan_c.dw >> 2), c4 = i - rp * (plan_c.dw >> 2);
     *reinterpret_cast<float4 *>(shlut + rp * d.hstride + 4 * c4) = __ldg(reinterpret_cast<const float4 *>(&A.hlut[rp >> 2][rp & 3][4 * c4]));
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
       const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, (unsigned)inv) : myi;
       const int dx = act ? f.y + myi - q * ncol : 0, dy = act ? f.z + q : 0;
       o = act ? dy * dw + dx : -1;
-      const int xs = __ldg(&plan->xs0[dx]), ys = __ldg(&plan->ys0[dy]);
+      const int xs = sxs[dx], ys = sys[dy];
       /* source rows as packed bytes: lo = taps 0..3, hi = tap 4 (TX == 5) */
       uint32_t lo[TY], hi[TY];
 #pragma unroll
@@ -249,14 +265,14 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
       }
       float al[TX];
 #pragma unroll
-      for (int t = 0; t < TX; t++) al[t] = __ldg(&plan->xalpha[t][dx]);
+      for (int t = 0; t < TX; t++) al[t] = sxa[t * ps + dx];
       float acc = 0.0f;
 #pragma unroll
       for (int k = 0; k < TY; k++) {
         float h = tbx_fmul(tbx_u8f(lo[k] & 255u), al[0]);
 #pragma unroll
         for (int t = 1; t < TX; t++) h = tbx_fadd(h, tbx_fmul(tbx_u8f(t < 4 ? (lo[k] >> (8 * t)) & 255u : hi[k]), al[t]));
-        const float bh = tbx_fmul(__ldg(&plan->yalpha[k][dy]), h);
+        const float bh = tbx_fmul(sya[k * ps + dy], h);
         acc = k == 0 ? bh : tbx_fadd(acc, bh);
       }
       const int iv = tbx_f2i_rn_small(acc);
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
             const int sel = __ldg(&A.hsel[dy][k]);
             const float4 h = sel < nrows ? *reinterpret_cast<const float4 *>(hw + sel * hs + 4 * myword)
                                          : __ldg(reinterpret_cast<const float4 *>(&A.hstatic[sel - nrows][4 * myword]));
-            const float b = __ldg(&plan->yalpha[k][dy]);
+            const float b = sya[k * ps + dy];
             const float p0 = tbx_fmul(b, h.x), p1 = tbx_fmul(b, h.y), p2 = tbx_fmul(b, h.z), p3 = tbx_fmul(b, h.w);
             if (k == 0) { acc[0] = p0; acc[1] = p1; acc[2] = p2; acc[3] = p3; }
             else { acc[0] = tbx_fadd(acc[0], p0); acc[1] = tbx_fadd(acc[1], p1); acc[2] = tbx_fadd(acc[2], p2); acc[3] = tbx_fadd(acc[3], p3); }
