@@ -747,7 +747,10 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
   uint32_t *recw = reinterpret_cast<uint32_t *>(wmem);
   uint32_t *lk = reinterpret_cast<uint32_t *>(wmem + RECW_BYTES);             /* [31][2]: the tile rows as 2-bit looks */
   int4 *mrec = reinterpret_cast<int4 *>(wmem + RECW_BYTES + 256);             /* 3 x int4 per mover */
-  const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
+  /* two teams of 4 warps per CTA, as in the Breakout kernel: own chunks of 4 envs, record stages and barrier */
+  constexpr int TEAM = 4, TEAM_THREADS = TEAM * 32;
+  const int team = wid / TEAM, wt = wid % TEAM, ttid = tid % TEAM_THREADS;
+  const int n_chunks = (a.n + TEAM - 1) / TEAM;
   const int dw = cp.dw, dh = cp.dh, nwords = dw >> 2, nb = dw * dh;
   const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
   const int ok = A.ok, mdy0 = A.mdy0, mdy1 = A.mdy1, hud_dylo = A.hud_dylo;
@@ -755,33 +758,35 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
   const uint32_t glut = A.gray[0] | (A.gray[1] << 8) | (A.gray[2] << 16) | (A.gray[3] << 24); /* look -> gray, one byte each */
   const TbxDigitPatch *__restrict__ patches = a.patches[1];
 
+  uint32_t *tstage = stage + team * 2 * RW * TEAM; /* [2][RW][4 envs] */
   auto prefetch = [&](int chunk, int st) {
-    const uint32_t *src = a.planes + (size_t)chunk * TBX_EPC;
-    uint32_t *dst = stage + st * RW * TBX_EPC;
-    for (int i = tid; i < RW * 2; i += TBX_DIRECT_THREADS) cp_async16(dst + i * 4, src + (size_t)(i >> 1) * a.n_pad + (i & 1) * 4);
+    const uint32_t *src = a.planes + (size_t)chunk * TEAM;
+    uint32_t *dst = tstage + st * RW * TEAM;
+    for (int i = ttid; i < RW; i += TEAM_THREADS) cp_async16(dst + i * TEAM, src + (size_t)i * a.n_pad);
     cp_async_commit();
   };
-  /* dynamic chunk scheduling: CTA b starts with chunk b, further chunks come from a device-wide counter (thread 0 draws the
-   * id one iteration ahead; the barrier at the top of the loop publishes it), so the CTAs finish together whatever their envs cost */
-  __shared__ int s_next[2];
-  if (tid == 0) s_next[0] = (int)gridDim.x + atomicAdd(d.sched, 1);
-  if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x, 0);
+  /* dynamic chunk scheduling per team (see the Breakout kernel) */
+  __shared__ int s_next[2][2];
+  const int n_teams = (int)gridDim.x * (TBX_DIRECT_THREADS / TEAM_THREADS);
+  if (ttid == 0) s_next[team][0] = n_teams + atomicAdd(d.sched, 1);
+  if ((int)blockIdx.x * 2 + team < n_chunks) prefetch((int)blockIdx.x * 2 + team, 0);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const uint32_t *R = recw;
+  __syncthreads(); /* the staged base frame is complete */
 
   int st = 0, it = 0, nxt = 0;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk = nxt, st ^= 1, it++) {
+  for (int chunk = (int)blockIdx.x * 2 + team; chunk < n_chunks; chunk = nxt, st ^= 1, it++) {
     cp_async_wait_all();
-    __syncthreads();
-    nxt = s_next[it & 1];
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM_THREADS) : "memory"); /* the team's barrier */
+    nxt = s_next[team][it & 1];
     if (nxt < n_chunks) prefetch(nxt, st ^ 1);
-    if (tid == 0) s_next[(it + 1) & 1] = (int)gridDim.x + atomicAdd(d.sched, 1);
-    const int env = chunk * TBX_EPC + wid;
+    if (ttid == 0) s_next[team][(it + 1) & 1] = n_teams + atomicAdd(d.sched, 1);
+    const int env = chunk * TEAM + wt;
     if (env >= a.n) continue;
     {
-      const uint32_t *src = stage + st * RW * TBX_EPC + wid;
-      for (int w = lane; w < RW; w += 32) recw[w] = src[w * TBX_EPC];
+      const uint32_t *src = tstage + st * RW * TEAM + wt;
+      for (int w = lane; w < RW; w += 32) recw[w] = src[w * TEAM];
     }
     __syncwarp();
     uint8_t *out = a.dst + (size_t)env * a.env_stride + (size_t)a.stack_slot * a.frame_bytes;
@@ -1010,6 +1015,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
       if (o >= 0) out[o] = (uint8_t)v;
     }
   }
+  __syncthreads(); /* both teams have run dry */
   /* the last CTA to finish re-arms the chunk counter for the next launch */
   if (tid == 0) {
     __threadfence();
