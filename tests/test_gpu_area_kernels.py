@@ -298,3 +298,44 @@ def test_amidar_painted_corridors_every_layout(tbx, oracle_mod):
         for k in keys:
             os.environ.pop(k, None)
         pool.close()
+
+
+def test_si_score_strip_every_digit_pair(tbx, oracle_mod):
+    """Space Invaders' score is rendered as one strip from a table of digit pairs (neighbouring digits feed a common output column):
+    scores that put every pair of digits (and the empty slot) next to each other at every position, ten-digit scores, and states where
+    something else reaches into the strip (a laser, an invader: the digits are then evaluated with it) -- bit-exact, several sizes."""
+    scores = [0, 7, 10, 99, 100, 101, 909, 1000, 4711, 10000, 99999, 100000, 1234567, 7654321, 10000000, 98765432, 100000000, 123456789,
+              999999999, 1000000000, 1999999999, 2000000000, 2147483647]
+    for k in range(9):                     # digit a in slot k, digit b in slot k + 1, a leading 1 above where b is 0
+        for a in range(10):
+            for b in range(10):
+                v = a * 10 ** k + b * 10 ** (k + 1) + (10 ** (k + 2) if b == 0 and k + 2 <= 9 else 0)
+                if 0 < v <= 2147483647:
+                    scores.append(v)
+    scores = sorted(set(scores))
+    n = len(scores)
+    pool, ref = _advance(tbx, oracle_mod, "space_invaders", n, 40, 77)
+    rng = np.random.default_rng(9)
+    states = []
+    for i in range(n):
+        js = ref.state_json(i)
+        js["score"] = int(scores[i])
+        if i % 9 == 4:        # a laser through the score's rows
+            js["enemy_lasers"] = [{"x": int(rng.integers(40, 122)), "y": int(rng.integers(0, 8)), "w": 2, "h": 8, "t": 0, "movement": "Down", "speed": 3,
+                                   "color": {"r": 252, "g": 252, "b": 84, "a": 255}}]
+        if i % 9 == 7:        # an invader on top of it
+            js["enemies"][3]["x"], js["enemies"][3]["y"] = int(rng.integers(30, 120)), int(rng.integers(0, 6))
+        ref.write_state_json(i, js)
+        states.append(js)
+    pool.write_state_json(states)
+    try:
+        for ow, oh in ((84, 84), (96, 80), (64, 64), (48, 60), (128, 128)):
+            want = ref.render("gray84", ow, oh).reshape(n, -1)
+            for v in ({}, TILE):
+                _set_env(v)
+                got = pool.render(obs=("gray_area", ow, oh)).cpu().numpy().reshape(n, -1)
+                bad = np.argwhere(got != want)
+                assert bad.size == 0, (ow, oh, v, [scores[int(b[0])] for b in bad[:5]], bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
+    finally:
+        _set_env({})
+        pool.close()

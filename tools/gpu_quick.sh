@@ -1,5 +1,5 @@
 #!/bin/bash
+# quick single-GPU check
 set -x
 mkdir -p gpurun_out
-B="--no-cpu-baseline --no-e2e --no-protocol --no-states"
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:_direct -s 6 -c 1 -o gpurun_out/q_prof_brk4 python bench.py --game breakout --steps 4 --warmup 3 $B > gpurun_out/q_ncu_brk4.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_area_kernels.py -m gpu -q -x -k "si_ or score" > gpurun_out/q_pytest.log 2>&1; tail -5 gpurun_out/q_pytest.log

@@ -160,6 +160,8 @@ TBX_HD int tbx_digit_at(int value, int k) {
  * tap order. */
 #define TBX_SD_MAX_ENTRIES 72
 #define TBX_SD_MAX_SETS 16
+#define TBX_SC_MAX_COLS 32
+#define TBX_SC_MAX_ROWS 4
 #define TBX_SP_MAX_W 6
 #define TBX_SP_MAX_H 5
 typedef struct TbxSpritePatch { uint8_t w, h; uint8_t px[TBX_SP_MAX_W * TBX_SP_MAX_H]; } TbxSpritePatch; /* 32 bytes; pixel (r, c) at px[r * TBX_SP_MAX_W + c] */
@@ -176,6 +178,14 @@ typedef struct TbxSiDirect {
   uint8_t set_lut[16][4];             /* per bank sprite ((off - 50) / 10, explosions 8 + (off - 127) / 10): up to 4 candidate sets, 255 = none */
   uint32_t inv32[TBX_AREA_MAX_DST + 1]; /* ceil(2^32 / n) for n >= 2 */
   uint32_t plain[TBX_AREA_MAX_DST][4]; /* per output row: the output columns all of whose real taps are background in base frame 0 */
+  /* THE SCORE AS ONE STRIP.  Its digits are 8 source pixels apart, so neighbouring digits feed a common output column and no
+   * digit can be a patch of its own.  But an output column is fed by at most two neighbouring digit slots: sc_px holds every
+   * pixel of the strip for every pair of digits (10 = no digit) in those two slots, resolved on the host from base frame 0 with
+   * the digits drawn.  sc_ok == 0: the geometry does not allow it (the digits are then evaluated pixel by pixel). */
+  int32_t sc_ok, sc_gray;
+  int32_t sc_dx0, sc_ncol, sc_dy0, sc_nrow;            /* output pixels fed by the ten digit slots */
+  uint8_t sc_slot[TBX_SC_MAX_COLS];                    /* per strip column: the lowest slot that feeds it (255: none) */
+  uint8_t sc_px[TBX_SC_MAX_COLS][11][11][TBX_SC_MAX_ROWS]; /* [column][digit in that slot][digit in the next slot][row] */
 } TbxSiDirect;
 /* patch of set s at phase (x mod px_period, y mod py_period): patches[(s * py_period + yphase) * px_period + xphase] */
 

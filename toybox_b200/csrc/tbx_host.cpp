@@ -1060,6 +1060,71 @@ void build_brk_direct(const Config &c, const BrkTable &t, const ResizeTab &rs, c
   A.ok = 1;
 }
 
+/* Space Invaders: the score strip (TbxSiDirect.sc_*): every output pixel the ten digit slots feed, for every pair of digits in the (at
+ * most two, neighbouring) slots that feed its column */
+static void build_si_score_strip(const ResizeTab &rs, const TbxAreaPlan &pl, const uint8_t *base0, TbxSiDirect &A) {
+  const int W = TBX_SI_W, H = TBX_SI_H;
+  A.sc_ok = 0;
+  A.sc_gray = (int32_t)tbx_luma(SI_COLOR_HUD);
+  std::vector<uint32_t> rec(TBX_WORDS(SiRec), 0);
+  TbxHdr &hd = *reinterpret_cast<TbxHdr *>(rec.data());
+  /* the boxes of the ten slots (a score of ten digits shows them all) */
+  int bx0[TBX_MAX_DIGITS], bx1[TBX_MAX_DIGITS], by0 = 0, by1 = 0;
+  hd.score = 1999999999;
+  for (int k = 0; k < TBX_MAX_DIGITS; k++) {
+    const TbxPrim p = si_prim(rec.data(), SI_SLOT_SCORE + k);
+    if (p.h <= 0 || p.bw != 3 || p.x < 0 || p.y < 0 || p.x + p.w > W || p.y + p.h > H) return;
+    if (k > 0 && (p.y != by0 || p.y + p.h != by1 || p.x + p.w > bx0[k - 1])) return; /* one row of boxes, right to left */
+    bx0[k] = p.x; bx1[k] = p.x + p.w; by0 = p.y; by1 = p.y + p.h;
+  }
+  const int dx0 = pl.xdlo[bx0[TBX_MAX_DIGITS - 1]], dx1 = pl.xdhi[bx1[0] - 1], dy0 = pl.ydlo[by0], dy1 = pl.ydhi[by1 - 1];
+  const int ncol = dx1 - dx0 + 1, nrow = dy1 - dy0 + 1;
+  if (ncol < 1 || ncol > TBX_SC_MAX_COLS || nrow < 1 || nrow > TBX_SC_MAX_ROWS) return;
+  std::vector<uint8_t> gray(base0, base0 + (size_t)W * H);
+  const uint8_t lum = (uint8_t)A.sc_gray;
+  for (int c = 0; c < ncol; c++) {
+    const int dx = dx0 + c;
+    /* the slots whose boxes the column's real taps read */
+    int lo = -1, hi = -1;
+    for (int k = 0; k < TBX_MAX_DIGITS; k++) {
+      bool touch = false;
+      for (int kx = rs.x.start[dx]; kx < rs.x.start[dx + 1]; kx++) touch |= rs.x.si[kx] >= bx0[k] && rs.x.si[kx] < bx1[k];
+      if (touch) { if (lo < 0) lo = k; hi = k; }
+    }
+    if (hi > lo + 1) return; /* three slots under one column: not this table's case */
+    A.sc_slot[c] = lo < 0 ? 255 : (uint8_t)lo;
+    for (int da = 0; da <= 10; da++)
+      for (int db = 0; db <= 10; db++) {
+        /* a score that shows digit da in slot lo and db in slot lo + 1 (10: the slot is empty); impossible pairs keep the base */
+        bool possible = lo >= 0 && da < 10 && !(db == 10 && da == 0 && lo > 0) && !(db < 10 && lo + 1 >= TBX_MAX_DIGITS);
+        long long v = 0;
+        if (possible) {
+          long long pw = 1;
+          for (int i = 0; i < lo; i++) pw *= 10;
+          v = da * pw + (db < 10 ? db * pw * 10 : 0);
+          if (db == 0) v += pw * 100;                  /* a leading zero needs a digit above it */
+          if (v > 2147483647LL) possible = false;
+          if (db == 0 && lo + 2 >= TBX_MAX_DIGITS) possible = false;
+        }
+        if (possible) {
+          hd.score = (int32_t)v;
+          for (int k = lo; k <= lo + 1 && k < TBX_MAX_DIGITS; k++) {
+            const TbxPrim p = si_prim(rec.data(), SI_SLOT_SCORE + k);
+            if (p.h <= 0) continue;
+            for (int y = p.y; y < p.y + p.h; y++)
+              for (int x = p.x; x < p.x + p.w; x++)
+                if (tbx_prim_covers(p, HOST_BANK, rec.data(), x, y)) gray[(size_t)y * W + x] = lum;
+          }
+        }
+        for (int r = 0; r < nrow; r++) A.sc_px[c][da][db][r] = area_pixel(gray.data(), W, rs, dx, dy0 + r);
+        if (possible)
+          for (int y = by0; y < by1; y++) memcpy(&gray[(size_t)y * W + bx0[TBX_MAX_DIGITS - 1]], base0 + (size_t)y * W + bx0[TBX_MAX_DIGITS - 1], (size_t)(bx1[0] - bx0[TBX_MAX_DIGITS - 1]));
+      }
+  }
+  A.sc_dx0 = dx0; A.sc_ncol = ncol; A.sc_dy0 = dy0; A.sc_nrow = nrow;
+  A.sc_ok = 1;
+}
+
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 /* Space Invaders: the sprite patch tables and the plain-background map of one output size (tbx_direct.h).  `patches`
  * receives n_sets * py_period * px_period entries (empty when the tables would be too large: n_sets = 0). */
@@ -1084,6 +1149,7 @@ void build_si_direct(const Config &c, const ResizeTab &rs, const TbxAreaPlan &pl
   A.inv_px = A.px_period > 1 ? 0xffffffffu / (uint32_t)A.px_period + 1u : 0u;
   A.inv_py = A.py_period > 1 ? 0xffffffffu / (uint32_t)A.py_period + 1u : 0u;
   A.ok = 1;
+  build_si_score_strip(rs, pl, base0, A);
   /* the patches rely on the tap tables repeating exactly (start offsets and f32 weights, bit for bit): check, do not assume */
   for (int dx = 0; dx + A.ox_period < dw; dx++) {
     if (pl.xs0[dx + A.ox_period] != pl.xs0[dx] + A.px_period) return;

@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
 #define TBX_SI_DIRECT_MIN_CTAS 3
 #define TBX_E_SPRITE_PATCH 1u
 #define TBX_E_DIGIT_PATCH 2u
+#define TBX_E_SCORE 4u /* a digit of the score: rendered with the others as one strip (TbxSiDirect.sc_px) */
 #ifdef TBX_SI_STATS
 __device__ unsigned long long d_si_stats[48];
 #endif
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
   const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
   const int n_sets = A.n_sets, pxp = A.px_period, pyp = A.py_period;
   const uint32_t inv_px = A.inv_px, inv_py = A.inv_py;
+  const int sc_ok = A.sc_ok, sc_gray = A.sc_gray, sc_dx0 = A.sc_dx0, sc_ncol = A.sc_ncol, sc_dy0 = A.sc_dy0, sc_nrow = A.sc_nrow;
   const uint32_t *__restrict__ base0w = reinterpret_cast<const uint32_t *>(a.base[0]);
   const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
     }
     /* 1. entries */
     for (int i = lane; i < 2 * dh * ow; i += 32) occ1[i] = 0;
-    int n = 0;
+    int n = 0, n_sc = 0, ufx0 = 255, ufx1 = -1, ufy0 = 255, ufy1 = -1; /* the score's digits as one strip: their count, their footprints' union */
     for (int s0 = SI_N_STATIC; s0 < SI_N_SLOTS; s0 += 32) {
       const int slot = s0 + lane;
       TbxPrim p = tbx_prim_none();
@@ -482,12 +484,16 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       const int x0 = max((int)p.x, 0), y0 = max((int)p.y, 0), x1 = min((int)p.x + (int)p.w, W), y1 = min((int)p.y + (int)p.h, H);
       const bool ok = p.h > 0 && x0 < x1 && y0 < y1;
       const unsigned m = __ballot_sync(0xffffffffu, ok);
+      bool is_sc = false;
+      int fx0 = 255, fx1 = -1, fy0 = 255, fy1 = -1;
       if (ok) {
-        const int fx0 = __ldg(&plan->xdlo[x0]), fx1 = __ldg(&plan->xdhi[x1 - 1]), fy0 = __ldg(&plan->ydlo[y0]), fy1 = __ldg(&plan->ydhi[y1 - 1]);
+        fx0 = __ldg(&plan->xdlo[x0]); fx1 = __ldg(&plan->xdhi[x1 - 1]); fy0 = __ldg(&plan->ydlo[y0]); fy1 = __ldg(&plan->ydhi[y1 - 1]);
         const uint32_t gray = tbx_luma(p.color);
         uint32_t kind = 0, ref = 0;
         const bool whole = p.x >= 0 && p.y >= 0 && (int)p.x + (int)p.w <= W && (int)p.y + (int)p.h <= H;
-        if (whole && p.bw == 3 && slot < SI_SLOT_SHIELDS && p.off < TBX_BANK_FONT + 50 && dpatch) { /* a HUD digit */
+        if (sc_ok && whole && p.bw == 3 && slot < SI_SLOT_LIVES && p.off < TBX_BANK_FONT + 50 && (int)gray == sc_gray) { /* a digit of the score */
+          kind = TBX_E_SCORE; is_sc = true;
+        } else if (whole && p.bw == 3 && slot < SI_SLOT_SHIELDS && p.off < TBX_BANK_FONT + 50 && dpatch) { /* a HUD digit */
           ref = (uint32_t)(slot - SI_SLOT_SCORE) * 10u + p.off / 5u;
           if (__ldg(&dpatch[ref].w) != 0) kind = TBX_E_DIGIT_PATCH;
         } else if (whole && n_sets && p.bw == 16 && p.scale == 0x11 && !(p.off & TBX_PRIM_STATE) && p.off >= TBX_BANK_INVADER) { /* a bank sprite: is there a patch set for (sprite, gray)? */
@@ -504,10 +510,25 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
         ent[2 * e + 1] = make_int4((int)((uint32_t)p.off | ((uint32_t)p.bw << 16) | ((uint32_t)p.scale << 24)), fx0 | (fx1 << 8) | (fy0 << 16) | (fy1 << 24), 0, slot);
       }
       n += __popc(m);
+      if (s0 == SI_N_STATIC && sc_ok) { /* the score's slots are among the first 32 */
+        n_sc = __popc(__ballot_sync(0xffffffffu, is_sc));
+        ufx0 = __reduce_min_sync(0xffffffffu, is_sc ? fx0 : 255); ufx1 = __reduce_max_sync(0xffffffffu, is_sc ? fx1 : -1);
+        ufy0 = __reduce_min_sync(0xffffffffu, is_sc ? fy0 : 255); ufy1 = __reduce_max_sync(0xffffffffu, is_sc ? fy1 : -1);
+      }
     }
     __syncwarp();
-    /* 2. which entries share an output pixel with another one */
+    /* 2. which entries share an output pixel with another one.  The score's digits count as ONE entry, the union of their footprints
+     * (neighbouring digits always share a column: the strip table below knows every pair) */
+    if (n_sc && lane <= ufy1 - ufy0) {
+      const int r = ufy0 + lane;
+      for (int w = ufx0 >> 5; w <= ufx1 >> 5; w++) {
+        const uint32_t mask = (w == ufx0 >> 5 ? 0xffffffffu << (ufx0 & 31) : 0xffffffffu) & (w == ufx1 >> 5 ? 0xffffffffu >> (31 - (ufx1 & 31)) : 0xffffffffu);
+        const uint32_t dup = atomicOr(&occ1[r * ow + w], mask) & mask;
+        if (dup) atomicOr(&occ2[r * ow + w], dup);
+      }
+    }
     for (int e = lane; e < n; e += 32) {
+      if ((((uint32_t)ent[2 * e].w >> 8) & 255u) == TBX_E_SCORE) continue;
       const uint32_t fp = (uint32_t)ent[2 * e + 1].y;
       const int fx0 = fp & 255u, fx1 = (fp >> 8) & 255u, fy0 = (fp >> 16) & 255u, fy1 = fp >> 24;
       for (int w = fx0 >> 5; w <= fx1 >> 5; w++) {
@@ -519,6 +540,16 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       }
     }
     __syncwarp();
+    bool sc_shared = false; /* something else touches the score's strip: its digits are then evaluated like any overlapping entries */
+    if (n_sc) {
+      bool hit = false;
+      if (lane <= ufy1 - ufy0)
+        for (int w = ufx0 >> 5; w <= ufx1 >> 5; w++) {
+          const uint32_t mask = (w == ufx0 >> 5 ? 0xffffffffu << (ufx0 & 31) : 0xffffffffu) & (w == ufx1 >> 5 ? 0xffffffffu >> (31 - (ufx1 & 31)) : 0xffffffffu);
+          hit |= (occ2[(ufy0 + lane) * ow + w] & mask) != 0;
+        }
+      sc_shared = __any_sync(0xffffffffu, hit);
+    }
     int n_eval = 0, total = 0;
     bool any_shared = false;
     for (int e0 = 0; e0 < n; e0 += 32) {
@@ -531,6 +562,8 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
         area = (fx1 - fx0 + 1) * (fy1 - fy0 + 1);
         const uint32_t kind = ((uint32_t)ent[2 * e].w >> 8) & 255u;
         bool plain = true; /* sprite patches assume background around them; digit patches were resolved on the base itself */
+        if (kind == TBX_E_SCORE) shared = sc_shared;
+        else
         for (int w = fx0 >> 5; w <= fx1 >> 5 && !shared; w++) {
           const uint32_t mask = (w == fx0 >> 5 ? 0xffffffffu << (fx0 & 31) : 0xffffffffu) & (w == fx1 >> 5 ? 0xffffffffu >> (31 - (fx1 & 31)) : 0xffffffffu);
           for (int r = fy0; r <= fy1; r++) {
@@ -539,7 +572,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
           }
         }
         patch = kind != 0 && !shared && plain;
-        if (patch) ent[2 * e + 1].z = 1; /* rendered as a patch below */
+        if (patch && kind != TBX_E_SCORE) ent[2 * e + 1].z = 1; /* rendered as a patch below (the score: as a strip) */
       }
       const unsigned em = __ballot_sync(0xffffffffu, e < n && !patch);
       if (e < n && !patch) { const int k = n_eval + __popc(em & lt_mask); lst[k] = e | (shared ? 0x10000 : 0); lcnt[k] = area; }
@@ -591,6 +624,23 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
         const int pw = __ldg(&P->w), ph = __ldg(&P->h);
         for (int r = 0; r < ph; r++)
           for (int c = 0; c < pw; c++) o[r * dw + c] = __ldg(&P->px[r * pw + c]);
+      }
+    }
+    /* 2c. the score's strip: every pixel its digits feed, looked up by the digits of the (at most two) slots over its column */
+    if (n_sc && !sc_shared) {
+      const int ncu = ufx1 - ufx0 + 1, tot = ncu * (ufy1 - ufy0 + 1);
+      const int32_t score = (int32_t)R[TBX_HW(score)];
+      const uint32_t inv = ncu > 1 ? __ldg(&A.inv32[ncu]) : 0u;
+      for (int i = lane; i < tot; i += 32) {
+        const int r = ncu > 1 ? (int)__umulhi((unsigned)i, inv) : i, c = i - r * ncu;
+        const int dx = ufx0 + c, dy = ufy0 + r, tc = dx - sc_dx0, tr = dy - sc_dy0;
+        if (tc < 0 || tc >= sc_ncol || tr < 0 || tr >= sc_nrow) continue;
+        const int k0 = __ldg(&A.sc_slot[tc]);
+        if (k0 == 255) continue;
+        int da = tbx_digit_at(score, k0), db = k0 + 1 < TBX_MAX_DIGITS ? tbx_digit_at(score, k0 + 1) : -1;
+        if (da < 0) da = 10;
+        if (db < 0) db = 10;
+        out[dy * dw + dx] = __ldg(&A.sc_px[tc][da][db][tr]);
       }
     }
     /* 3. the evaluated entries' pixels.  A pixel of an entry that shares no output pixel with another one sees that entry
