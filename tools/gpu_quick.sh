@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick single-GPU check
+# quick single-GPU check: the area-kernel and parity tests
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_area_kernels.py -m gpu -q -x -k "si_ or score" > gpurun_out/q_pytest.log 2>&1; tail -5 gpurun_out/q_pytest.log
+timeout 900 python -m pytest tests/test_gpu_area_kernels.py tests/test_gpu_parity.py tests/test_gpu_full_size.py -m gpu -q -x > gpurun_out/q_pytest.log 2>&1; tail -3 gpurun_out/q_pytest.log

@@ -29,6 +29,7 @@ namespace tbxk {
 /* pitch / bytes of the plan tables the Breakout kernel keeps behind its other shared memory */
 __host__ __device__ __forceinline__ int brk_plan_pitch(int dw, int dh) { return ((dw > dh ? dw : dh) + 3) & ~3; }
 __host__ __device__ __forceinline__ int brk_plan_smem_bytes(int tx, int ty, int dw, int dh) { return ((tx + ty) * brk_plan_pitch(dw, dh) * 4 + 2 * brk_plan_pitch(dw, dh) * 2 + 15) & ~15; }
+__host__ __device__ __forceinline__ int si_tab_smem_bytes(int dw, int dh) { return ((dh * ((dw + 31) >> 5) + 3) & ~3) * 4 + ((TBX_AREA_MAX_DST + 1 + 3) & ~3) * 4; }
 __device__ __forceinline__ int brk_dig_cid(int slot) { return slot < 4 ? slot : slot >= TBX_MAX_DIGITS && slot < TBX_MAX_DIGITS + 2 ? slot - TBX_MAX_DIGITS + 4 : -1; }
 #define TBX_BRK_TAB_BYTES (TBX_BRK_DIG_BYTES + TBX_BD_MAX_CLS * TBX_BRK_W + 16 + TBX_BRK_H + (TBX_AREA_MAX_DST + 1 + 3) / 4 * 16)
 #ifndef TBX_DIRECT_MIN_CTAS
@@ -433,6 +434,9 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
   uint32_t *occ2 = occ1 + dh * ow;                                               /* covered by two or more */
   int *lst = reinterpret_cast<int *>(occ2 + dh * ow);                            /* evaluated entries: id, then pixel count */
   int *lcnt = lst + TBX_SD_MAX_ENTRIES;
+  /* two small hot tables behind everything else (si_tab_smem_bytes: the launch adds them to d.smem_total) */
+  uint32_t *splain = reinterpret_cast<uint32_t *>(smem + d.smem_total);          /* [dh][ow]: TbxSiDirect.plain */
+  uint32_t *sinv = splain + ((dh * ow + 3) & ~3);                                /* inv32[] */
   const int n_chunks = (a.n + TBX_EPC - 1) / TBX_EPC;
   const bool bulk = (nb & 15) == 0 && (a.env_stride & 15) == 0 && (a.frame_bytes & 15) == 0;
   const int n_sets = A.n_sets, pxp = A.px_period, pyp = A.py_period;
@@ -451,6 +455,8 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
   if ((int)blockIdx.x < n_chunks) prefetch(blockIdx.x);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[0]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int i = tid; i < dh * ow; i += TBX_DIRECT_THREADS) splain[i] = __ldg(&A.plain[i / ow][i % ow]);
+  for (int i = tid; i <= TBX_AREA_MAX_DST; i += TBX_DIRECT_THREADS) sinv[i] = __ldg(&A.inv32[i]);
   const uint32_t *R = recw;
 
   int it = 0, nxt = 0;
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
           const uint32_t mask = (w == fx0 >> 5 ? 0xffffffffu << (fx0 & 31) : 0xffffffffu) & (w == fx1 >> 5 ? 0xffffffffu >> (31 - (fx1 & 31)) : 0xffffffffu);
           for (int r = fy0; r <= fy1; r++) {
             if (occ2[r * ow + w] & mask) { shared = true; break; }
-            if (kind == TBX_E_SPRITE_PATCH && (__ldg(&A.plain[r][w]) & mask) != mask) plain = false;
+            if (kind == TBX_E_SPRITE_PATCH && (splain[r * ow + w] & mask) != mask) plain = false;
           }
         }
         patch = kind != 0 && !shared && plain;
@@ -630,7 +636,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
     if (n_sc && !sc_shared) {
       const int ncu = ufx1 - ufx0 + 1, tot = ncu * (ufy1 - ufy0 + 1);
       const int32_t score = (int32_t)R[TBX_HW(score)];
-      const uint32_t inv = ncu > 1 ? __ldg(&A.inv32[ncu]) : 0u;
+      const uint32_t inv = ncu > 1 ? sinv[ncu] : 0u;
       for (int i = lane; i < tot; i += 32) {
         const int r = ncu > 1 ? (int)__umulhi((unsigned)i, inv) : i, c = i - r * ncu;
         const int dx = ufx0 + c, dy = ufy0 + r, tc = dx - sc_dx0, tr = dy - sc_dy0;
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_SI_DIRECT_MIN_CTAS) si
       const uint32_t fp = (uint32_t)ent[2 * (mine & 0xffff) + 1].y;
       const int fx0 = fp & 255u, fx1 = (fp >> 8) & 255u, fy0 = (fp >> 16) & 255u;
       const int ncol = fx1 - fx0 + 1;
-      const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, __ldg(&A.inv32[ncol])) : myi;
+      const int q = ncol > 1 ? (int)__umulhi((unsigned)myi, sinv[ncol]) : myi;
       const int dx = act ? fx0 + myi - q * ncol : 0, dy = act ? fy0 + q : 0;
       const int xs = __ldg(&plan->xs0[dx]), ys = __ldg(&plan->ys0[dy]);
       uint32_t lo[TY], hi[TY];
