@@ -6,13 +6,13 @@
  * kernel (tbx_render_area.cuh, env-list mode) renders right after.
  *
  * Breakout, per env (warp):
- *   1. frame <- pre-computed down-sample of base frame 1 (every brick alive), 16-byte copies;
+ *   1. frame <- pre-computed down-sample of base frame 1 (every brick alive), one bulk copy from shared memory;
  *   2. if a brick is dead: the wall's H rows (one look-up per brick row and output column) go to shared memory and the
  *      output words (4 pixels) x rows that a dead brick feeds are recomputed from them -- cost bounded by the wall's
  *      output area, whatever the number of holes;
  *   3. HUD digits: pre-resolved patches;
- *   4. paddle and balls: the output pixels their rectangles feed, every tap evaluated analytically
- *      (brk_direct_pixel: base frame 0, brick grid, movers in draw order).
+ *   4. paddle and balls: the output pixels their rectangles feed, their source windows built as packed bytes
+ *      (base frame 0, brick grid, movers in draw order) and resolved in cv2's tap order.
  */
 #ifndef TBX_RENDER_DIRECT_CUH
 #define TBX_RENDER_DIRECT_CUH
@@ -43,10 +43,12 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-/* PERSISTENT CTAs: CTA b renders the chunks (8 consecutive envs, one per warp) b, b + gridDim.x, ...  Shared memory:
- * the down-sample of base frame 1 (loaded once per CTA; every env's frame starts as ONE bulk shared -> global copy of it,
- * cp.async.bulk, no per-env load/store instructions), two stages of word-major records (cp.async prefetch of the next
- * chunk), and per warp its env's record, the wall's H rows and the movers' records. */
+/* PERSISTENT CTAs of two 4-warp TEAMS: a team renders chunks of 4 consecutive envs (one per warp), its first chunk fixed, the
+ * next ones drawn from a device-wide counter.  Shared memory: the down-sample of base frame 1 (loaded once per CTA; every env's
+ * frame starts as ONE bulk shared -> global copy of it, cp.async.bulk, no per-env load/store instructions); the small tables the
+ * per-pixel code indexes (digit patches of the slots in use, base frame 0 by row classes, the wall's H look-up, the plan's weights
+ * and first-source indices, a division table: L1 is too small next to this much shared memory to keep them); per team two stages
+ * of word-major records (cp.async prefetch of the next chunk); per warp its env's record, the wall's H rows, the movers' records. */
 template <int TX, int TY>
 __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_direct_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ BrkCfg cfg_c,
                                                                             const __grid_constant__ TbxAreaPlan plan_c, const __grid_constant__ DirectArgs d) {
