@@ -215,6 +215,8 @@ int emu_render_direct(Emu *e, int out_w, int out_h, uint8_t *out) {
   tbx::build_brk_direct(e->cfg, dt, rs, pl, base0.data(), A);
   const uint32_t *R = e->rec.data();
   if (!A.ok || (int32_t)R[TBX_HW(tbl)] != e->cfg.brk.default_tbl) return 1;
+  for (int y = 0; y < H && A.n_cls > 0; y++) /* base frame 0 by row classes: what the kernel's mover windows read */
+    if (A.rowcls[y] >= A.n_cls || memcmp(A.clsrows + (size_t)A.rowcls[y] * W, base0.data() + (size_t)y * W, W) != 0) { g_err = "row class table differs from base frame 0"; return -1; }
   std::vector<TbxDigitPatch> patches((size_t)TBX_DP_SLOTS * 10);
   tbx::build_digit_patches(e->cfg, &dt, rs, pl, base1.data(), patches.data());
   TbxMover mv[BRK_N_MOVERS];
@@ -273,6 +275,51 @@ int emu_render_direct(Emu *e, int out_w, int out_h, uint8_t *out) {
       for (int dx = fx0[m]; dx <= fx1[m]; dx++)
         out[dy * out_w + dx] = brk_direct_pixel<TBX_AREA_MAX_TAPS, TBX_AREA_MAX_TAPS>(A, pl, base0.data(), alive, mv, near, wall, dx, dy);
   }
+  return 0;
+}
+
+/* Space Invaders' score strip (TbxSiDirect.sc_*, si_direct_kernel step 2c) on the host: the full-frame reference with the pixels the
+ * score's digits feed overwritten from the digit-pair table, exactly as the kernel indexes it.  Must equal emu_render(mode 3) whenever
+ * nothing else reaches into the strip.  Returns 1 when the table does not exist for this size (out = the reference then). */
+int emu_si_score_strip(Emu *e, int out_w, int out_h, uint8_t *out) {
+  if (e->game != TBX_SPACE_INVADERS) { g_err = "space_invaders only"; return -1; }
+  const int W = e->info->width, H = e->info->height;
+  if (emu_render(e, 3, out_w, out_h, out) != 0) return -1;
+  tbx::ResizeTab rs;
+  TbxAreaPlan pl;
+  try { tbx::build_resize(W, H, out_w, out_h, rs); } catch (const std::exception &ex) { g_err = ex.what(); return -1; }
+  if (!tbx::build_area_plan(rs, pl)) return 1;
+  std::vector<uint32_t> rgba((size_t)W * H);
+  std::vector<uint8_t> base0((size_t)W * H);
+  tbx::build_base_frame(e->cfg, 0, 0, rgba.data());
+  tbx::frame_to_gray(rgba.data(), W * H, base0.data());
+  static TbxSiDirect A;
+  std::vector<TbxSpritePatch> sp;
+  tbx::build_si_direct(e->cfg, rs, pl, base0.data(), A, sp);
+  if (!A.ok || !A.sc_ok) return 1;
+  const uint32_t *R = e->rec.data();
+  int ufx0 = 255, ufx1 = -1, ufy0 = 255, ufy1 = -1, n_sc = 0;
+  for (int slot = SI_SLOT_SCORE; slot < SI_SLOT_LIVES; slot++) {
+    const TbxPrim p = si_prim(R, slot);
+    if (p.h <= 0) continue;
+    if (p.bw != 3 || (int)tbx_luma(p.color) != A.sc_gray || p.x < 0 || p.y < 0 || p.x + p.w > W || p.y + p.h > H) return 1;
+    const int fx0 = pl.xdlo[p.x], fx1 = pl.xdhi[p.x + p.w - 1], fy0 = pl.ydlo[p.y], fy1 = pl.ydhi[p.y + p.h - 1];
+    ufx0 = fx0 < ufx0 ? fx0 : ufx0; ufx1 = fx1 > ufx1 ? fx1 : ufx1; ufy0 = fy0 < ufy0 ? fy0 : ufy0; ufy1 = fy1 > ufy1 ? fy1 : ufy1;
+    n_sc++;
+  }
+  if (!n_sc) return 1;
+  const int32_t score = (int32_t)R[TBX_HW(score)];
+  for (int dy = ufy0; dy <= ufy1; dy++)
+    for (int dx = ufx0; dx <= ufx1; dx++) {
+      const int tc = dx - A.sc_dx0, tr = dy - A.sc_dy0;
+      if (tc < 0 || tc >= A.sc_ncol || tr < 0 || tr >= A.sc_nrow) continue;
+      const int k0 = A.sc_slot[tc];
+      if (k0 == 255) continue;
+      int da = tbx_digit_at(score, k0), db = k0 + 1 < TBX_MAX_DIGITS ? tbx_digit_at(score, k0 + 1) : -1;
+      if (da < 0) da = 10;
+      if (db < 0) db = 10;
+      out[dy * out_w + dx] = A.sc_px[tc][da][db][tr];
+    }
   return 0;
 }
 

@@ -117,6 +117,16 @@ class Emu:
             raise ValueError(self.L.emu_last_error().decode())
         return None if rc else out
 
+    def si_score_strip(self, out_w=84, out_h=84):
+        """Space Invaders: the reference frame with the score's pixels taken from the digit-pair table (TbxSiDirect.sc_px), as the
+        direct kernel does; None when the table does not exist for this size."""
+        out = np.empty((out_h, out_w), np.uint8)
+        self.L.emu_si_score_strip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        rc = self.L.emu_si_score_strip(self.h, out_w, out_h, out.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            raise ValueError(self.L.emu_last_error().decode())
+        return None if rc else out
+
     def state_json(self):
         return json.loads(_take(self.L.emu_state_to_json(self.h)))
 

@@ -97,3 +97,34 @@ def test_direct_hands_over_what_it_does_not_cover(oracle_mod):
     for t in range(600):
         b.step(ale_action=_track(b, t), auto_reset=True)
     assert np.array_equal(b.render_direct(), b.render("gray84"))
+
+
+@pytest.mark.parametrize("size", [(84, 84), (96, 80), (64, 64), (48, 60), (128, 128)])
+def test_si_score_strip_table_equals_full_resize(size):
+    """Space Invaders: the score rendered as one strip from the host-built table of digit pairs (TbxSiDirect.sc_px, the direct kernel's
+    step 2c, emulated on the host) equals the full-frame resize for scores that put every pair of digits (and the empty slot) next
+    to each other at every position, single digits and ten-digit scores."""
+    scores = [0, 7, 10, 99, 100, 101, 909, 1000, 4711, 99999, 1234567, 98765432, 123456789, 999999999, 1000000000, 1999999999, 2147483647]
+    for k in range(9):
+        for a in range(10):
+            for b in range(10):
+                v = a * 10 ** k + b * 10 ** (k + 1) + (10 ** (k + 2) if b == 0 and k + 2 <= 9 else 0)
+                if 0 < v <= 2147483647:
+                    scores.append(v)
+    e = emu_lib.Emu("space_invaders")
+    e.seed(5)
+    e.new_game()
+    js = e.state_json()
+    ow, oh = size
+    n_table = 0
+    for v in sorted(set(scores)):
+        js["score"] = int(v)
+        e.write_state_json(js)
+        want = e.render("gray84", ow, oh)
+        got = e.si_score_strip(ow, oh)
+        if got is None:
+            continue
+        n_table += 1
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (size, v, bad[:4], got[tuple(bad[0])], want[tuple(bad[0])])
+    assert n_table > 0 or size != (84, 84)          # the table exists at the size the benchmark uses
