@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) brk_d
   float *sya = sxa + TX * ps;                                                   /* [TY][ps] */
   uint16_t *sxs = reinterpret_cast<uint16_t *>(sya + TY * ps), *sys = sxs + ps; /* xs0, ys0 */
   __shared__ int s_bigdig;
-  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2][RW][8 envs] */
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + d.smem_base);           /* [2 teams][2 stages][RW][4 envs] */
   const TbxBrkDirect *__restrict__ Ap = reinterpret_cast<const TbxBrkDirect *>(d.aux);
   const TbxBrkDirect &A = *Ap;
   const TbxAreaPlan *__restrict__ plan = a.plan; /* per-lane indexed reads */
