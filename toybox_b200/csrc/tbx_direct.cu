@@ -121,12 +121,13 @@ template <int TX, int TY> static cudaError_t launch_si(const RenderArgs &a, cons
 }
 
 template <int TX, int TY> static cudaError_t launch_ami(const RenderArgs &a, const TbxAreaPlan &plan, const DirectArgs &d, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(ami_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_total);
+  const int smem = d.smem_total + ami_tab_smem_bytes(plan.dh); /* three small per-pixel tables go behind the rest */
+  cudaError_t e = cudaFuncSetAttribute(ami_direct_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int grid = 1;
-  e = persistent_grid(ami_direct_kernel<TX, TY>, d.smem_total, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
+  e = persistent_grid(ami_direct_kernel<TX, TY>, smem, (a.n + TBX_EPC - 1) / TBX_EPC, &grid);
   if (e != cudaSuccess) return e;
-  ami_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, d.smem_total, s>>>(a, plan, d);
+  ami_direct_kernel<TX, TY><<<grid, TBX_DIRECT_THREADS, smem, s>>>(a, plan, d);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,7 @@ namespace tbxk {
 __host__ __device__ __forceinline__ int brk_plan_pitch(int dw, int dh) { return ((dw > dh ? dw : dh) + 3) & ~3; }
 __host__ __device__ __forceinline__ int brk_plan_smem_bytes(int tx, int ty, int dw, int dh) { return ((tx + ty) * brk_plan_pitch(dw, dh) * 4 + 2 * brk_plan_pitch(dw, dh) * 2 + 15) & ~15; }
 __host__ __device__ __forceinline__ int si_tab_smem_bytes(int dw, int dh) { return ((dh * ((dw + 31) >> 5) + 3) & ~3) * 4 + ((TBX_AREA_MAX_DST + 1 + 3) & ~3) * 4; }
+__host__ __device__ __forceinline__ int ami_tab_smem_bytes(int dh) { return TBX_AMI_W + 256 + ((dh * 4 + 15) & ~15); }
 __device__ __forceinline__ int brk_dig_cid(int slot) { return slot < 4 ? slot : slot >= TBX_MAX_DIGITS && slot < TBX_MAX_DIGITS + 2 ? slot - TBX_MAX_DIGITS + 4 : -1; }
 #define TBX_BRK_TAB_BYTES (TBX_BRK_DIG_BYTES + TBX_BD_MAX_CLS * TBX_BRK_W + 16 + TBX_BRK_H + (TBX_AREA_MAX_DST + 1 + 3) / 4 * 16)
 #ifndef TBX_DIRECT_MIN_CTAS
@@ -805,6 +806,10 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
   uint32_t *recw = reinterpret_cast<uint32_t *>(wmem);
   uint32_t *lk = reinterpret_cast<uint32_t *>(wmem + RECW_BYTES);             /* [31][2]: the tile rows as 2-bit looks */
   int4 *mrec = reinterpret_cast<int4 *>(wmem + RECW_BYTES + 256);             /* 3 x int4 per mover */
+  /* three small per-pixel tables behind everything else (ami_tab_smem_bytes: the launch adds them to d.smem_total) */
+  uint8_t *sxcol = smem + d.smem_total;                                       /* [W]: TbxAmiDirect.xcol */
+  uint8_t *syrow = sxcol + TBX_AMI_W;                                         /* [H rounded up to 256]: yrow */
+  uint32_t *sdyr = reinterpret_cast<uint32_t *>(syrow + 256);                 /* [dh]: dyrows */
   /* two teams of 4 warps per CTA, as in the Breakout kernel: own chunks of 4 envs, record stages and barrier */
   constexpr int TEAM = 4, TEAM_THREADS = TEAM * 32;
   const int team = wid / TEAM, wt = wid % TEAM, ttid = tid % TEAM_THREADS;
@@ -830,8 +835,11 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
   if ((int)blockIdx.x * 2 + team < n_chunks) prefetch((int)blockIdx.x * 2 + team, 0);
   for (int i = tid; i < ((nb + 15) >> 4); i += TBX_DIRECT_THREADS) reinterpret_cast<uint4 *>(sbase)[i] = __ldg(reinterpret_cast<const uint4 *>(a.base_out[1]) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int i = tid; i < W / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(sxcol)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.xcol) + i);
+  for (int i = tid; i < 256 / 4; i += TBX_DIRECT_THREADS) reinterpret_cast<uint32_t *>(syrow)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.yrow) + i);
+  for (int i = tid; i < plan_c.dh; i += TBX_DIRECT_THREADS) sdyr[i] = __ldg(&A.dyrows[i]);
   const uint32_t *R = recw;
-  __syncthreads(); /* the staged base frame is complete */
+  __syncthreads(); /* the staged base frame and the tables are complete */
 
   int st = 0, it = 0, nxt = 0;
   for (int chunk = (int)blockIdx.x * 2 + team; chunk < n_chunks; chunk = nxt, st ^= 1, it++) {
@@ -962,10 +970,10 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
       /* the source window from the tile looks: packed bytes, taps 0..3 of each row */
       uint32_t cb[TX], lo[TY];
 #pragma unroll
-      for (int t = 0; t < TX; t++) cb[t] = __ldg(&A.xcol[min(xs + t, W - 1)]);
+      for (int t = 0; t < TX; t++) cb[t] = sxcol[min(xs + t, W - 1)];
 #pragma unroll
       for (int k = 0; k < TY; k++) {
-        const uint32_t r = __ldg(&A.yrow[min(ys + k, H - 1)]);
+        const uint32_t r = syrow[min(ys + k, H - 1)];
         uint32_t row = g0 * 0x01010101u;
         if (r != 255u) {
           const uint32_t w0 = lk[2 * r], w1 = lk[2 * r + 1];
@@ -1025,7 +1033,7 @@ __global__ void __launch_bounds__(TBX_DIRECT_THREADS, TBX_DIRECT_MIN_CTAS) ami_d
         if (myword >= 0) c04 = __ldg(reinterpret_cast<const uint32_t *>(A.col0) + myword); /* col0 of the word's four columns */
         for (int dyb = mdy0; dyb <= mdy1; dyb += rpi) {
           const int dy = dyb + sub;
-          const bool on = myword >= 0 && dy <= mdy1 && (__ldg(&A.dyrows[min(dy, dh - 1)]) & rowsm) != 0;
+          const bool on = myword >= 0 && dy <= mdy1 && (sdyr[min(dy, dh - 1)] & rowsm) != 0;
           if (!on) continue;
           float acc[4];
 #pragma unroll
